@@ -1,0 +1,124 @@
+"""Pin the CPU oracle to outputs of the UNMODIFIED reference (tests/golden/*.npz, made by
+tests/golden/make_golden.py in the build container) and, when /root/reference is present, to the
+reference run live."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hmvit_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def checksum(t):
+    return float(t.double().abs().sum())
+
+
+def rel_l2(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+def test_index_tables_bit_exact():
+    g = np.load(os.path.join(GOLDEN, "index.npz"))
+    for (H, W) in ((48, 176), (128, 128), (96, 352), (16, 24)):
+        for kind in ("window", "grid"):
+            ref = torch.from_numpy(g[f"{kind}_{H}x{W}"]).long()
+            assert torch.equal(O.group_token_table(H, W, 8, kind), ref), (kind, H, W)
+    assert torch.equal(O.relative_position_index(8), torch.from_numpy(g["relative_position_index"]))
+
+
+def test_regroup_mask_bit_exact():
+    g = np.load(os.path.join(GOLDEN, "index.npz"))
+    dense = torch.randn(6, 2, 4, 4, generator=torch.Generator().manual_seed(5))
+    feat, m = O.regroup(dense, torch.tensor([1, 3, 2]), 4)
+    assert m.dtype == torch.int64 and torch.equal(m, torch.from_numpy(g["regroup_mask"]))
+    assert checksum(feat) == pytest.approx(float(g["regroup_feat_checksum"][0]), rel=1e-12)
+    assert feat.shape == (3, 4, 2, 4, 4) and float(feat[0, 1:].abs().sum()) == 0.0
+
+
+def test_partition_rejects_non_divisible():
+    with pytest.raises(ValueError):
+        O.partition_index(50, 176, 8, "window")
+
+
+def test_warp_and_mask_vs_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "warp_mask.npz"))
+    B, L, C, H, W = 2, 4, 2, 48, 176
+    x, T, mode, record_len, mask = O.synth_inputs(B, L, C, H, W, [4, 3], 31)
+    assert checksum(x) == pytest.approx(float(g["in_checksum"][0]), rel=1e-9)
+    assert checksum(T) == pytest.approx(float(g["in_checksum"][1]), rel=1e-9)
+    warped = torch.from_numpy(g["warped"])                       # (B, src, tgt, C, H, W)
+    shape = tuple(int(v) for v in g["mask_shape"])
+    mask_pair = torch.from_numpy(np.unpackbits(g["mask_pair"])[: int(np.prod(shape))].reshape(shape)).float()
+    mism = 0
+    for i in range(L):
+        y = O.spatial_transformation(x, T[:, :, i], 0.4, 4)
+        # reference's own fp32 normalise/inverse chain is ~1e-4 abs off the closed form
+        assert (y - warped[:, :, i]).abs().max() < 5e-4
+        assert rel_l2(y, warped[:, :, i]) < 1e-4
+        m = O.roi_and_cav_mask((B, L, H, W, C), mask, T[:, :, i], 0.4, 4)
+        mism += int((m != mask_pair[..., i]).sum())
+    assert mism == 0                                              # bit exact on this seed
+
+
+def test_attention_vs_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "attention.npz"))
+    C, b, l, X, Y, w = 256, 2, 3, 2, 2, 8
+    gen = torch.Generator().manual_seed(21)
+    P = O.synth_state_dict(O.default_config(input_dim=C), 21)
+    x = torch.randn(b, l, X, Y, w, w, C, generator=gen)
+    assert checksum(x) == pytest.approx(float(g["x_checksum"][0]), rel=1e-9)
+    mode = torch.from_numpy(g["mode"])
+    mask = torch.from_numpy(g["mask"]).float()                   # (b, X, Y, w, w, 1, l)
+    ref = torch.from_numpy(g["out"])                             # (b, 1, X, Y, w, w, C)
+    for bi in range(b):
+        xw = x[bi].reshape(l, X * Y, w * w, C)
+        km = mask[bi, ..., 0, :].permute(4, 0, 1, 2, 3).reshape(l, X * Y, w * w)
+        y = O.hetero_attention_ego(xw, mode[bi], 0, km, P, "hetero_fusion_block.grid_attention")
+        assert rel_l2(y.reshape(X, Y, w, w, C), ref[bi, 0]) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["fusion_c64", "fusion_c256"])
+def test_fusion_vs_reference_golden(name):
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    C, B, L, H, W, seed = (int(v) for v in g["meta"][:6])
+    tx, ty = float(g["meta"][6]), float(g["meta"][7])
+    cfg = O.default_config(input_dim=C)
+    P = O.synth_state_dict(cfg, seed)
+    assert sum(checksum(v) for v in P.values()) == pytest.approx(float(g["p_checksum"][0]), rel=1e-9)
+    x, T, mode, record_len, mask = O.synth_inputs(B, L, C, H, W, g["record_len"].tolist(), seed + 100, tx=tx, ty=ty)
+    assert checksum(x) == pytest.approx(float(g["in_checksum"][0]), rel=1e-9)
+    fused = O.hetero_fusion(x, T, mode, record_len, mask, P, cfg)
+    assert rel_l2(fused, torch.from_numpy(g["fused"])) < 1e-5
+    blk = O.fusion_block(x, T, mode.long(), record_len, mask, P, cfg["hetero_fusion_block"])
+    ref_blk = torch.from_numpy(g["block"])
+    for b in range(B):                                           # every slot, padded ones included
+        assert rel_l2(blk[b], ref_blk[b]) < 1e-5
+
+
+def test_state_dict_spec_matches_default_module_keys():
+    spec = O.state_dict_spec(O.default_config())
+    keys = [k for k, _ in spec]
+    assert len(keys) == 88 and len(set(keys)) == 88
+    n_param = sum(int(np.prod(s)) for k, s in spec if not k.endswith("relative_position_index"))
+    assert n_param == 2506256
+
+
+@pytest.mark.reference
+def test_oracle_vs_live_reference():
+    import ref_import
+    if not ref_import.available():
+        pytest.skip("reference tree not present (GPU box)")
+    R = ref_import.load()
+    cfg = O.default_config()
+    P = O.synth_state_dict(cfg, 3)
+    ref = R.HeteroFusion(cfg).eval()
+    assert list(ref.state_dict().keys()) == [k for k, _ in O.state_dict_spec(cfg)]
+    ref.load_state_dict(P, strict=True)
+    x, T, mode, record_len, mask = O.synth_inputs(2, 4, 256, 16, 16, [4, 2], 77, tx=8, ty=6)
+    with torch.no_grad():
+        yr = ref(x.clone(), T.clone(), mode.clone(), record_len, mask)
+    yo = O.hetero_fusion(x, T, mode, record_len, mask, P, cfg)
+    assert rel_l2(yo, yr) < 1e-5
