@@ -1,0 +1,14 @@
+"""hmvit_b200 -- B200 (sm_100a) native HM-ViT multi-agent BEV fusion hot path.
+
+The directory is called `hm-vit_b200` (not importable by name); load it with `hmvit_loader.load()`
+from the repo root, which registers it as the module `hmvit_b200`.
+"""
+from . import _lib, ops  # noqa: F401
+from .fusion import (HeteroAttention, HeteroFeedForward, HeteroFusion, HeteroFusionBlock,  # noqa: F401
+                     HeteroLayerNorm, HeteroPreNormResidual, SpatialTransformation,
+                     get_roi_and_cav_mask, regroup)
+from .build import build_extension  # noqa: F401
+
+__all__ = ["HeteroFusion", "HeteroFusionBlock", "HeteroAttention", "HeteroLayerNorm", "HeteroFeedForward",
+           "HeteroPreNormResidual", "SpatialTransformation", "get_roi_and_cav_mask", "regroup",
+           "build_extension", "ops"]

@@ -1,0 +1,102 @@
+"""ctypes binding of libhmvit_b200.so (C-ABI declared in include/hmvit_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+Build the library with `python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhmvit_b200.so")
+
+GEMM_QKV, GEMM_OUT, GEMM_FFN1, GEMM_FFN2, GEMM_HEAD1, GEMM_HEAD2, GEMM_QKV_NOLN = range(7)
+
+EXPORTS = (
+    "hmvit_abi_version", "hmvit_last_error", "hmvit_rowgemm", "hmvit_group_attn", "hmvit_warp_bilinear",
+    "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
+    "hmvit_debug_probe",
+)
+
+
+class RowGemmArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("N", C.c_int32), ("n_out", C.c_int32),
+                ("mode", C.c_void_p), ("record_len", C.c_void_p), ("ego_only", C.c_int32),
+                ("a", C.c_void_p), ("w", C.c_void_p * 2), ("bias", C.c_void_p),
+                ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float),
+                ("resid", C.c_void_p), ("out", C.c_void_p)]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("kind", C.c_int32), ("ego_only", C.c_int32),
+                ("mode", C.c_void_p), ("record_len", C.c_void_p), ("cav_mask", C.c_void_p), ("T", C.c_void_p),
+                ("cell", C.c_double), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+                ("bk", C.c_void_p), ("bv", C.c_void_p), ("bias_table", C.c_void_p), ("key_mask", C.c_void_p),
+                ("out", C.c_void_p)]
+
+
+class StageWeights(C.Structure):
+    _fields_ = [("wqkv", C.c_void_p * 2), ("bqkv", C.c_void_p), ("bk", C.c_void_p), ("bv", C.c_void_p),
+                ("wa", C.c_void_p * 2), ("ba", C.c_void_p),
+                ("ln1_g", C.c_void_p), ("ln1_b", C.c_void_p), ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p),
+                ("w1", C.c_void_p * 2), ("b1", C.c_void_p), ("w2", C.c_void_p * 2), ("b2", C.c_void_p),
+                ("bias_table", C.c_void_p)]
+
+
+class FusionArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("num_iters", C.c_int32), ("head", C.c_int32), ("skip_dead", C.c_int32),
+                ("x", C.c_void_p), ("T", C.c_void_p), ("mode", C.c_void_p), ("record_len", C.c_void_p),
+                ("cav_mask", C.c_void_p), ("cell", C.c_double), ("ln_eps", C.c_float),
+                ("stage", StageWeights * 2),
+                ("head_w1", C.c_void_p * 2), ("head_b1", C.c_void_p), ("head_w2", C.c_void_p * 2), ("head_b2", C.c_void_p),
+                ("xres", C.c_void_p), ("workspace", C.c_void_p), ("out", C.c_void_p)]
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run __graft_entry__.build() "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU / eager fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.hmvit_abi_version.restype = C.c_int
+    lib.hmvit_last_error.restype = C.c_char_p
+    lib.hmvit_rowgemm.argtypes = [C.c_int, C.POINTER(RowGemmArgs), C.c_void_p]
+    lib.hmvit_rowgemm.restype = C.c_int
+    lib.hmvit_group_attn.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+    lib.hmvit_group_attn.restype = C.c_int
+    lib.hmvit_warp_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                        C.c_double, C.c_void_p]
+    lib.hmvit_warp_bilinear.restype = C.c_int
+    lib.hmvit_roi_cav_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_double, C.c_void_p]
+    lib.hmvit_roi_cav_mask.restype = C.c_int
+    lib.hmvit_fusion_workspace_bytes.argtypes = [C.c_int32] * 4
+    lib.hmvit_fusion_workspace_bytes.restype = C.c_size_t
+    lib.hmvit_fusion_forward.argtypes = [C.POINTER(FusionArgs), C.c_void_p]
+    lib.hmvit_fusion_forward.restype = C.c_int
+    lib.hmvit_fusion_launch_count.argtypes = [C.c_int32, C.c_int32]
+    lib.hmvit_fusion_launch_count.restype = C.c_int
+    lib.hmvit_debug_probe.argtypes = [C.c_void_p, C.c_void_p]
+    lib.hmvit_debug_probe.restype = C.c_int
+    if lib.hmvit_abi_version() != 1:
+        raise ImportError("libhmvit_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+class HmvitError(RuntimeError):
+    pass
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().hmvit_last_error()
+        raise HmvitError(msg.decode() if msg else f"hmvit error {rc}")

@@ -1,0 +1,302 @@
+// Fused multi-agent group attention for one (scene b, ego agent i, token group g).
+//
+// Replaces the reference's warp_features + per-ego HeteroAttention.forward core
+// (hetero_fusion.py:338-361, 187-277): the warped copies x_pair (B,L,L,C,H,W) and the mask_pair
+// tensor are never materialised.  For every source agent j the kernel
+//   1. evaluates the j->i source-pixel map for the group's 64 tokens (fp64, like the oracle), the
+//      nearest-neighbour ROI visibility (bit-exact key mask) and the 4 bilinear taps;
+//   2. gathers the PROJECTED keys / values of agent j (edge-type weights already folded into the
+//      projection) with 16-byte vector loads, blends the taps in fp32, adds the folded
+//      bias, rounds to bf16 and stores them swizzled in shared memory;
+//   3. runs S = Q K^T (+ relative position bias, key mask), an online softmax over all sources and
+//      O += P V on the tensor cores, fp32 accumulation, one warp per 16 query rows and all 8 heads.
+// Sources with no visible key in this group are skipped entirely (their softmax weight is exactly 0).
+// window / grid partition differ only in the token table (hetero_fusion.py:384-389 vs 427-431).
+//
+// Round-1 note: the contractions use warp-level mma.sync (HMMA) tiles; the kernel is bound by the
+// gather (L2 -> SM traffic), see DESIGN.md.  A tcgen05 version is the next step for this kernel.
+#pragma once
+#include "common.cuh"
+
+namespace hmvit {
+
+struct AttnParams {
+  int B, L, H, W;
+  int kind;                    // 0 = window partition, 1 = grid partition
+  int ego_only;                // 1: only ego slot 0 of each scene
+  const int* mode;             // [B*L]
+  const int* record_len;       // [B]
+  const int* cav_mask;         // [B*L]
+  const float* T;              // [B][L][L][16]  pairwise_t_matrix, [b][j][i] maps j -> i
+  double cell;                 // voxel_size[0] * downsample_rate (metres per BEV cell)
+  const __nv_bfloat16* q;      // [B*L*N][256]
+  const __nv_bfloat16* k;      // [2 (te)][B*L*N][256]
+  const __nv_bfloat16* v;      // [2 (te)][B*L*N][256]
+  const float* bk;             // [2 (te)][2 (tj)][256] folded key bias (added after the gather)
+  const float* bv;             // [2 (te)][2 (tj)][256]
+  const float* bias_table;     // [225][8] relative_position_bias_table.weight
+  const uint8_t* key_mask;     // optional [B*L][N]: extra per-token key mask of source j (unit-level API), or null
+  __nv_bfloat16* out;          // [B*L*N][256]
+};
+
+constexpr int kAttnThreads = 128;
+constexpr int kTileBytes = kS * kC * 2;          // 32 KB: 64 tokens x 256 ch bf16
+constexpr int kBiasStride = 232;                 // [8 heads][225 (+7 pad)]
+struct TapRec { int x0, y0; float w00, w01, w10, w11; int vis; int pad; };
+constexpr int kAttnSmem = 3 * kTileBytes + kHeads * kBiasStride * 4 + kS * sizeof(TapRec);
+
+// element (row, 16-byte unit) of a [64][512 B] tile, XOR-swizzled so ldmatrix is conflict free
+HMVIT_DEVINL uint32_t tile_off(int row, int unit) { return row * 512 + ((unit ^ (row & 7)) << 4); }
+
+HMVIT_DEVINL void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+HMVIT_DEVINL void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+HMVIT_DEVINL void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+HMVIT_DEVINL float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// flat token index of slot s in group (gy, gx)
+HMVIT_DEVINL void group_token(int kind, int gy, int gx, int s, int H, int W, int& r, int& c) {
+  const int s1 = s >> 3, s2 = s & 7;
+  if (kind == 0) { r = gy * kWin + s1; c = gx * kWin + s2; }
+  else           { r = s1 * (H / kWin) + gy; c = s2 * (W / kWin) + gx; }
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnParams p) {
+  const int a = blockIdx.y;
+  const int b = a / p.L, i = a - b * p.L;
+  const int nrec = p.record_len[b];
+  if (i >= nrec || (p.ego_only && i != 0)) return;
+  const int N = p.H * p.W;
+  const int GX = p.W / kWin;
+  const int gy = blockIdx.x / GX, gx = blockIdx.x - gy * GX;
+  const int te = p.mode[a] != 0 ? 1 : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + kTileBytes;
+  uint8_t* sV = smem + 2 * kTileBytes;
+  float* sBias = reinterpret_cast<float*>(smem + 3 * kTileBytes);          // [8][kBiasStride]
+  TapRec* sTap = reinterpret_cast<TapRec*>(sBias + kHeads * kBiasStride);  // [64]
+
+  // ---- stage Q (ego rows) and the bias table ----
+  {
+    const uint4* qsrc = reinterpret_cast<const uint4*>(p.q) + static_cast<size_t>(a) * N * 32;
+#pragma unroll 4
+    for (int tt = 0; tt < 16; ++tt) {
+      const int s = warp * 16 + tt;
+      int r, c; group_token(p.kind, gy, gx, s, p.H, p.W, r, c);
+      const uint4 v = __ldg(qsrc + static_cast<size_t>(r * p.W + c) * 32 + lane);
+      *reinterpret_cast<uint4*>(sQ + tile_off(s, lane)) = v;
+    }
+    for (int e = threadIdx.x; e < 225 * kHeads; e += kAttnThreads) {
+      const int idx = e >> 3, h = e & 7;
+      sBias[h * kBiasStride + idx] = __ldg(p.bias_table + e) * 1.4426950408889634f;   // log2(e) folded
+    }
+  }
+
+  float o[kHeads][4][4];
+  float mrow[kHeads][2], lrow[kHeads][2];
+#pragma unroll
+  for (int h = 0; h < kHeads; ++h) {
+    mrow[h][0] = mrow[h][1] = -INFINITY; lrow[h][0] = lrow[h][1] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { o[h][n][0] = o[h][n][1] = o[h][n][2] = o[h][n][3] = 0.f; }
+  }
+
+  const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+  const size_t plane = static_cast<size_t>(p.B) * p.L * N * 32;            // uint4 units per te plane
+
+  for (int j = 0; j < nrec; ++j) {
+    if (p.cav_mask[b * p.L + j] == 0) continue;
+    // ---- taps + visibility for the 64 tokens of this group, source j -> ego i ----
+    int vis = 0;
+    if (threadIdx.x < kS) {
+      const WarpMap wm = make_warp_map(p.T + ((static_cast<size_t>(b) * p.L + j) * p.L + i) * 16, p.H, p.W, p.cell);
+      int r, c; group_token(p.kind, gy, gx, threadIdx.x, p.H, p.W, r, c);
+      double sx, sy; warp_src(wm, c, r, sx, sy);
+      vis = warp_visible(sx, sy, p.H, p.W) ? 1 : 0;
+      if (p.key_mask != nullptr && p.key_mask[static_cast<size_t>(b * p.L + j) * N + r * p.W + c] == 0) vis = 0;
+      const Taps tp = make_taps(sx, sy, p.H, p.W);
+      TapRec rec; rec.x0 = tp.x0; rec.y0 = tp.y0; rec.w00 = tp.w00; rec.w01 = tp.w01; rec.w10 = tp.w10; rec.w11 = tp.w11;
+      rec.vis = vis; rec.pad = 0;
+      sTap[threadIdx.x] = rec;
+    }
+    if (!__syncthreads_or(vis)) continue;      // also orders sTap writes / previous compute phase
+
+    // ---- gather projected K / V rows of source j (bilinear, + folded bias) ----
+    {
+      const int tj = p.mode[b * p.L + j] != 0 ? 1 : 0;
+      const uint4* ksrc = reinterpret_cast<const uint4*>(p.k) + te * plane + static_cast<size_t>(b * p.L + j) * N * 32 + lane;
+      const uint4* vsrc = reinterpret_cast<const uint4*>(p.v) + te * plane + static_cast<size_t>(b * p.L + j) * N * 32 + lane;
+      float bkr[8], bvr[8];
+      {
+        const float4* pk = reinterpret_cast<const float4*>(p.bk + (te * 2 + tj) * kC + lane * 8);
+        const float4* pv = reinterpret_cast<const float4*>(p.bv + (te * 2 + tj) * kC + lane * 8);
+        const float4 k0 = __ldg(pk), k1 = __ldg(pk + 1), v0 = __ldg(pv), v1 = __ldg(pv + 1);
+        bkr[0] = k0.x; bkr[1] = k0.y; bkr[2] = k0.z; bkr[3] = k0.w; bkr[4] = k1.x; bkr[5] = k1.y; bkr[6] = k1.z; bkr[7] = k1.w;
+        bvr[0] = v0.x; bvr[1] = v0.y; bvr[2] = v0.z; bvr[3] = v0.w; bvr[4] = v1.x; bvr[5] = v1.y; bvr[6] = v1.z; bvr[7] = v1.w;
+      }
+#pragma unroll 2
+      for (int tt = 0; tt < 16; ++tt) {
+        const int s = warp * 16 + tt;
+        const TapRec rec = sTap[s];
+        float ka[8], va[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ka[e] = 0.f; va[e] = 0.f; }
+        if (rec.vis) {
+          const float w4[4] = {rec.w00, rec.w01, rec.w10, rec.w11};
+          uint4 kk[4], vv[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int yy = rec.y0 + (q >> 1), xx = rec.x0 + (q & 1);
+            kk[q] = make_uint4(0, 0, 0, 0); vv[q] = make_uint4(0, 0, 0, 0);
+            if (w4[q] != 0.f) {
+              const size_t off = static_cast<size_t>(yy * p.W + xx) * 32;
+              kk[q] = __ldg(ksrc + off); vv[q] = __ldg(vsrc + off);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float w = w4[q];
+            ka[0] += w * bf16_lo(kk[q].x); ka[1] += w * bf16_hi(kk[q].x); ka[2] += w * bf16_lo(kk[q].y); ka[3] += w * bf16_hi(kk[q].y);
+            ka[4] += w * bf16_lo(kk[q].z); ka[5] += w * bf16_hi(kk[q].z); ka[6] += w * bf16_lo(kk[q].w); ka[7] += w * bf16_hi(kk[q].w);
+            va[0] += w * bf16_lo(vv[q].x); va[1] += w * bf16_hi(vv[q].x); va[2] += w * bf16_lo(vv[q].y); va[3] += w * bf16_hi(vv[q].y);
+            va[4] += w * bf16_lo(vv[q].z); va[5] += w * bf16_hi(vv[q].z); va[6] += w * bf16_lo(vv[q].w); va[7] += w * bf16_hi(vv[q].w);
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { ka[e] += bkr[e]; va[e] += bvr[e]; }
+        }
+        uint4 ko, vo;
+        ko.x = pack_bf16x2(ka[0], ka[1]); ko.y = pack_bf16x2(ka[2], ka[3]); ko.z = pack_bf16x2(ka[4], ka[5]); ko.w = pack_bf16x2(ka[6], ka[7]);
+        vo.x = pack_bf16x2(va[0], va[1]); vo.y = pack_bf16x2(va[2], va[3]); vo.z = pack_bf16x2(va[4], va[5]); vo.w = pack_bf16x2(va[6], va[7]);
+        *reinterpret_cast<uint4*>(sK + tile_off(s, lane)) = ko;
+        *reinterpret_cast<uint4*>(sV + tile_off(s, lane)) = vo;
+      }
+    }
+    __syncthreads();
+
+    // ---- key visibility bits for this thread's columns: key s' = nt*8 + 2t + e ----
+    uint32_t vbits = 0;            // bit (nt*2 + e)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      vbits |= (sTap[nt * 8 + 2 * t].vis ? 1u : 0u) << (nt * 2);
+      vbits |= (sTap[nt * 8 + 2 * t + 1].vis ? 1u : 0u) << (nt * 2 + 1);
+    }
+
+    // ---- tensor-core phase: this warp's 16 query rows x all heads ----
+#pragma unroll
+    for (int h = 0; h < kHeads; ++h) {
+      float sacc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+      for (int kk2 = 0; kk2 < 2; ++kk2) {                       // 2 x k16 over the 32 head dims
+        uint32_t a0, a1, a2, a3;
+        {
+          const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int unit = h * 4 + kk2 * 2 + (lane >> 4);
+          ldsm_x4(sQ_u + tile_off(row, unit), a0, a1, a2, a3);
+        }
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {                        // pairs of key n-tiles
+          uint32_t b0, b1, b2, b3;
+          const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
+          const int unit = h * 4 + kk2 * 2 + ((lane >> 3) & 1);
+          ldsm_x4(sK_u + tile_off(row, unit), b0, b1, b2, b3);
+          mma_bf16(sacc[np * 2], a0, a1, a2, a3, b0, b1);
+          mma_bf16(sacc[np * 2 + 1], a0, a1, a2, a3, b2, b3);
+        }
+      }
+      // bias + mask (log2 domain), running max
+      const float* bh = sBias + h * kBiasStride;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int cs = 2 * t + e;                              // key column within its slot row nt
+          // query slot rows: 2*warp (row g) and 2*warp+1 (row g+8); query slot col = g
+          const int i0 = (2 * warp - nt + 7) * 15 + (g - cs + 7);
+          const bool ok = (vbits >> (nt * 2 + e)) & 1u;
+          const float x0 = ok ? fmaf(sacc[nt][e], 1.4426950408889634f, bh[i0]) : -INFINITY;
+          const float x1 = ok ? fmaf(sacc[nt][2 + e], 1.4426950408889634f, bh[i0 + 15]) : -INFINITY;
+          sacc[nt][e] = x0; sacc[nt][2 + e] = x1;
+          mx0 = fmaxf(mx0, x0); mx1 = fmaxf(mx1, x1);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(mrow[h][0], mx0), mn1 = fmaxf(mrow[h][1], mx1);
+      const float mu0 = (mn0 == -INFINITY) ? 0.f : mn0, mu1 = (mn1 == -INFINITY) ? 0.f : mn1;
+      const float al0 = ex2(mrow[h][0] - mu0), al1 = ex2(mrow[h][1] - mu1);
+      mrow[h][0] = mn0; mrow[h][1] = mn1;
+      float rs0 = 0.f, rs1 = 0.f;
+      uint32_t pa[4][4];                                         // P as A fragments: 4 x k16 over the 64 keys
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float p0 = ex2(sacc[nt][0] - mu0), p1 = ex2(sacc[nt][1] - mu0);
+        const float p2 = ex2(sacc[nt][2] - mu1), p3 = ex2(sacc[nt][3] - mu1);
+        rs0 += p0 + p1; rs1 += p2 + p3;
+        pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
+      rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+      rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+      lrow[h][0] = lrow[h][0] * al0 + rs0; lrow[h][1] = lrow[h][1] * al1 + rs1;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) { o[h][n][0] *= al0; o[h][n][1] *= al0; o[h][n][2] *= al1; o[h][n][3] *= al1; }
+      // O_h += P V_h
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) {
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {                        // pairs of dim n-tiles
+          uint32_t b0, b1, b2, b3;
+          const int row = kc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int unit = h * 4 + np * 2 + (lane >> 4);
+          ldsm_x4_t(sV_u + tile_off(row, unit), b0, b1, b2, b3);
+          mma_bf16(o[h][np * 2], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], b0, b1);
+          mma_bf16(o[h][np * 2 + 1], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], b2, b3);
+        }
+      }
+    }
+    __syncthreads();     // compute phase done before sTap / sK / sV are rewritten for the next source
+  }
+
+  // ---- normalise, stage in smem (reuse sK after a barrier), coalesced store ----
+  __syncthreads();
+#pragma unroll
+  for (int h = 0; h < kHeads; ++h) {
+    const float il0 = lrow[h][0] > 0.f ? 1.0f / lrow[h][0] : 0.f;
+    const float il1 = lrow[h][1] > 0.f ? 1.0f / lrow[h][1] : 0.f;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int col = h * kDh + n * 8 + 2 * t;                   // channel
+      const int r0 = warp * 16 + g, r1 = r0 + 8;
+      *reinterpret_cast<uint32_t*>(sK + tile_off(r0, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[h][n][0] * il0, o[h][n][1] * il0);
+      *reinterpret_cast<uint32_t*>(sK + tile_off(r1, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[h][n][2] * il1, o[h][n][3] * il1);
+    }
+  }
+  __syncthreads();
+  {
+    uint4* dst = reinterpret_cast<uint4*>(p.out) + static_cast<size_t>(a) * N * 32;
+#pragma unroll 4
+    for (int tt = 0; tt < 16; ++tt) {
+      const int s = warp * 16 + tt;
+      int r, c; group_token(p.kind, gy, gx, s, p.H, p.W, r, c);
+      dst[static_cast<size_t>(r * p.W + c) * 32 + lane] = *reinterpret_cast<const uint4*>(sK + tile_off(s, lane));
+    }
+  }
+}
+
+}  // namespace hmvit

@@ -1,0 +1,100 @@
+"""Thin Python wrappers over the C-ABI entry points (one per kernel family).
+
+torch is used for device memory and the current stream only; every arithmetic step of the fusion
+path happens inside libhmvit_b200.so.  All tensors must be CUDA, contiguous.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+C_DIM = 256
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype, name):
+    if not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (the B200 path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+def rowgemm(variant, *, B, L, N, n_out, mode, record_len, a, w0, w1, bias, out, ego_only=False,
+            ln_gamma=None, ln_beta=None, ln_eps=1e-5, resid=None):
+    args = _lib.RowGemmArgs()
+    args.B, args.L, args.N, args.n_out = B, L, N, n_out
+    args.mode = mode.data_ptr()
+    args.record_len = record_len.data_ptr()
+    args.ego_only = 1 if ego_only else 0
+    args.a = a.data_ptr()
+    args.w[0], args.w[1] = w0.data_ptr(), w1.data_ptr()
+    args.bias = bias.data_ptr()
+    args.ln_gamma = ln_gamma.data_ptr() if ln_gamma is not None else None
+    args.ln_beta = ln_beta.data_ptr() if ln_beta is not None else None
+    args.ln_eps = ln_eps
+    args.resid = resid.data_ptr() if resid is not None else None
+    args.out = out.data_ptr()
+    _lib.check(_lib.load().hmvit_rowgemm(variant, C.byref(args), _stream()))
+    return out
+
+
+def group_attn(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, k, v, bk, bv, bias_table, out,
+               ego_only=False, key_mask=None):
+    args = _lib.AttnArgs()
+    args.B, args.L, args.H, args.W = B, L, H, W
+    args.kind = kind
+    args.ego_only = 1 if ego_only else 0
+    args.mode, args.record_len, args.cav_mask = mode.data_ptr(), record_len.data_ptr(), cav_mask.data_ptr()
+    args.T = T.data_ptr()
+    args.cell = float(cell)
+    args.q, args.k, args.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    args.bk, args.bv, args.bias_table = bk.data_ptr(), bv.data_ptr(), bias_table.data_ptr()
+    args.key_mask = key_mask.data_ptr() if key_mask is not None else None
+    args.out = out.data_ptr()
+    _lib.check(_lib.load().hmvit_group_attn(C.byref(args), _stream()))
+    return out
+
+
+def warp_bilinear(x: torch.Tensor, T: torch.Tensor, cell: float) -> torch.Tensor:
+    """x (n, C, H, W) fp32, T (n, 4, 4) fp32 source->target.  Returns the warped maps (n, C, H, W)."""
+    _chk(x, torch.float32, "x"), _chk(T, torch.float32, "T")
+    n, Cc, H, W = x.shape
+    if T.shape != (n, 4, 4):
+        raise ValueError(f"T: expected shape {(n, 4, 4)}, got {tuple(T.shape)}")
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().hmvit_warp_bilinear(x.data_ptr(), T.data_ptr(), out.data_ptr(), n, Cc, H, W, float(cell), _stream()))
+    return out
+
+
+def roi_cav_mask(T: torch.Tensor, cav_mask: torch.Tensor, H: int, W: int, cell: float) -> torch.Tensor:
+    """T (B, L, 4, 4) fp32, cav_mask (B, L) int32 -> float32 (B, H, W, 1, L)."""
+    _chk(T, torch.float32, "T"), _chk(cav_mask, torch.int32, "cav_mask")
+    B, L = T.shape[:2]
+    out = torch.empty(B, H, W, 1, L, dtype=torch.float32, device=T.device)
+    _lib.check(_lib.load().hmvit_roi_cav_mask(T.data_ptr(), cav_mask.data_ptr(), out.data_ptr(), B, L, H, W, float(cell), _stream()))
+    return out
+
+
+def fusion_workspace_bytes(B, L, H, W) -> int:
+    return int(_lib.load().hmvit_fusion_workspace_bytes(B, L, H, W))
+
+
+def fusion_launch_count(num_iters, head) -> int:
+    return int(_lib.load().hmvit_fusion_launch_count(num_iters, 1 if head else 0))
+
+
+def debug_probe(device="cuda"):
+    out = torch.zeros(2, dtype=torch.int32, device=device)
+    _lib.check(_lib.load().hmvit_debug_probe(out.data_ptr(), _stream()))
+    return [int(v) & 0xFFFFFFFF for v in out.cpu().tolist()]

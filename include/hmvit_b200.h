@@ -1,0 +1,168 @@
+/* hmvit_b200 -- C ABI of the B200 (sm_100a) HM-ViT fusion hot path.
+ *
+ * The reference (XHwind/HM-ViT, a fork of OpenCOOD) has no C/FFI plugin interface: the boundary of
+ * this path is the Python nn.Module `HeteroFusion`
+ *   (opencood/models/bevformer_point_pillar_hetero.py:22-49, called at :122).
+ * This header is the C-ABI that a drop-in replacement of that module binds (ctypes stub shown in
+ * INTEGRATION.md; hm-vit_b200/_lib.py is the binding this repo ships).  Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller owns every buffer including the workspace (hmvit_fusion_workspace_bytes);
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t): no host synchronisation, no
+ *     allocation, CUDA-graph capturable;
+ *   - returns 0 on success, non-zero on error; hmvit_last_error() gives the message of the last
+ *     failing call on the calling thread.  No C++ exception crosses the boundary.
+ *
+ * Layouts.  N = H*W tokens per agent, C = 256 channels, L agent slots per scene.
+ *   "cm"   : fp32 [agents][256][N]      channel-major == the module's (B, L, C, H, W) layout
+ *   "rows" : bf16 [agents*N][256]       token-major rows (512 B per token)
+ *   mode       : int32 [B*L]   0 = camera, 1 = LiDAR (padded slots 0)
+ *   record_len : int32 [B]     valid agents per scene (>= 1)
+ *   cav_mask   : int32 [B*L]   regroup() mask (fuse_utils.py:8-61)
+ *   T          : fp32  [B][L][L][4][4]  pairwise_t_matrix, [b][i][j] maps agent i -> agent j
+ */
+#ifndef HMVIT_B200_H_
+#define HMVIT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMVIT_ABI_VERSION 1
+
+/* error codes */
+#define HMVIT_OK 0
+#define HMVIT_ERR_ARG 1      /* bad argument (shape not supported, null pointer, ...) */
+#define HMVIT_ERR_CUDA 2     /* a CUDA runtime / driver call failed */
+
+int hmvit_abi_version(void);
+const char* hmvit_last_error(void);
+
+/* ---- typed row-GEMM (grouped by agent modality) -------------------------------------------------
+ * Replaces the per-(b, agent) nn.Linear launches of
+ *   HeteroAttention.to_qkv / to_out        opencood/models/sub_modules/hetero_fusion.py:111-152
+ *   HeteroLayerNorm / HeteroFeedForward    opencood/models/base_transformer.py:138-192
+ *   HeteroFusion.mlp_head                  opencood/models/bevformer_point_pillar_hetero.py:47-48 */
+enum {
+  HMVIT_GEMM_QKV = 0,   /* A = LN_type(x cm) bf16; out rows bf16 [n_chunks/2][B*L*N][256] = A W^T + bias     */
+  HMVIT_GEMM_OUT = 1,   /* A = attention output rows bf16; out cm = A W^T + bias + resid cm                  */
+  HMVIT_GEMM_FFN1 = 2,  /* A = LN_type(x cm) tf32; out cm = tf32(gelu(A W^T + bias))                         */
+  HMVIT_GEMM_FFN2 = 3,  /* A = hidden cm tf32; out cm = A W^T + bias + resid cm                              */
+  HMVIT_GEMM_HEAD1 = 4, /* A = x cm tf32 (slot 0 only, no norm); out cm = tf32(gelu(A W^T + bias))           */
+  HMVIT_GEMM_HEAD2 = 5, /* A = hidden cm tf32 (slot 0 only); out [B][256][N] = A W^T + bias                  */
+  HMVIT_GEMM_QKV_NOLN = 6 /* like QKV but A = x cm cast to bf16 without LayerNorm (unit-level attention API)  */
+};
+
+typedef struct {
+  int32_t B, L, N;            /* scenes, slots per scene, tokens per agent */
+  int32_t n_out;              /* output channels of W (multiple of 128; 1280 for QKV, else 256) */
+  const int32_t* mode;        /* [B*L] */
+  const int32_t* record_len;  /* [B] */
+  int32_t ego_only;           /* QKV: Q only for slot 0 and K/V only for the ego type of slot 0;
+                                 other variants: process slot 0 tiles only */
+  const void* a;              /* A operand: fp32 cm, or bf16 rows for HMVIT_GEMM_OUT */
+  const void* w[2];           /* weights per modality type, row-major [n_out][256]: bf16 for QKV/OUT,
+                                 fp32 holding tf32-rounded values for the FFN and HEAD variants */
+  const float* bias;          /* [2][n_out] */
+  const float* ln_gamma;      /* [2][256] (QKV, FFN1) */
+  const float* ln_beta;       /* [2][256] */
+  float ln_eps;
+  const float* resid;         /* fp32 cm (OUT, FFN2) */
+  void* out;                  /* see variant */
+} HmvitRowGemmArgs;
+
+int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* args, void* stream);
+
+/* ---- fused warp + mask + multi-agent window / grid attention ---------------------------------------
+ * Replaces HeteroFusionBlock.warp_features + the ego loop around HeteroAttention.forward
+ *   opencood/models/sub_modules/hetero_fusion.py:338-361, 373-397 (window) / 412-440 (grid), 187-277
+ * and the warp / ROI-mask helpers it calls
+ *   opencood/models/sub_modules/torch_transformation_utils.py:11-134, 254-355. */
+typedef struct {
+  int32_t B, L, H, W;
+  int32_t kind;               /* 0 = window partition, 1 = grid partition */
+  int32_t ego_only;           /* only ego slot 0 of each scene */
+  const int32_t* mode;
+  const int32_t* record_len;
+  const int32_t* cav_mask;
+  const float* T;             /* [B][L][L][16] */
+  double cell;                /* voxel_size[0] * downsample_rate */
+  const void* q;              /* bf16 rows [B*L*N][256] (softmax scale folded into W_q) */
+  const void* k;              /* bf16 rows [2 (ego type)][B*L*N][256], relation_att folded */
+  const void* v;              /* bf16 rows [2 (ego type)][B*L*N][256], relation_msg folded */
+  const float* bk;            /* [2 (ego type)][2 (source type)][256] folded key bias */
+  const float* bv;            /* [2][2][256] folded value bias */
+  const float* bias_table;    /* [225][8] relative_position_bias_table.weight */
+  const uint8_t* key_mask;    /* optional [B*L][N] extra key mask indexed by (source slot, TARGET token); NULL = none.
+                                 Used by the unit-level HeteroAttention.forward surface (explicit mask argument). */
+  void* out;                  /* bf16 rows [B*L*N][256] */
+} HmvitAttnArgs;
+
+int hmvit_group_attn(const HmvitAttnArgs* args, void* stream);
+
+/* ---- stand-alone spatial warp and ROI mask (unit-parity surface) ------------------------------------
+ * SpatialTransformation.forward  opencood/models/sub_modules/spatial_transformation.py:16-44
+ *   x, out: fp32 [n][C][H][W]; T: fp32 [n][16] (source -> target); bilinear, zero padding.
+ * get_roi_and_cav_mask           opencood/models/sub_modules/torch_transformation_utils.py:11-49
+ *   out: fp32 [B][H][W][1][L] = nearest-warp visibility * cav_mask. */
+int hmvit_warp_bilinear(const float* x, const float* T, float* out, int32_t n, int32_t C, int32_t H, int32_t W,
+                        double cell, void* stream);
+int hmvit_roi_cav_mask(const float* T, const int32_t* cav_mask, float* out, int32_t B, int32_t L, int32_t H,
+                       int32_t W, double cell, void* stream);
+
+/* ---- whole fusion forward ----------------------------------------------------------------------------
+ * HeteroFusion.forward            opencood/models/bevformer_point_pillar_hetero.py:39-49
+ * HeteroFusionBlock.forward       opencood/models/sub_modules/hetero_fusion.py:446-458 (head == 0) */
+typedef struct {
+  const void* wqkv[2];        /* bf16 [1280][256] per source type: {Wq*scale, A(te=0)Wk, A(te=1)Wk, M(te=0)^T Wv, M(te=1)^T Wv} */
+  const float* bqkv;          /* [2][1280] (zero for the K / V columns) */
+  const float* bk;            /* [2][2][256] */
+  const float* bv;            /* [2][2][256] */
+  const void* wa[2];          /* bf16 [256][256] */
+  const float* ba;            /* [2][256] */
+  const float* ln1_g; const float* ln1_b;   /* attention pre-norm  [2][256] */
+  const float* ln2_g; const float* ln2_b;   /* feed-forward pre-norm [2][256] */
+  const void* w1[2];          /* fp32 (tf32) [256][256] */
+  const float* b1;            /* [2][256] */
+  const void* w2[2];          /* fp32 (tf32) [256][256] */
+  const float* b2;            /* [2][256] */
+  const float* bias_table;    /* [225][8] */
+} HmvitStageWeights;
+
+typedef struct {
+  int32_t B, L, H, W;
+  int32_t num_iters;          /* block applications (weights shared) */
+  int32_t head;               /* 1: ego slice + mlp_head -> out [B][256][N]; 0: stop after the blocks */
+  int32_t skip_dead;          /* 1 (with head): last grid stage computes ego-0 queries only (exact) */
+  const float* x;             /* fp32 cm [B*L][256][N], not modified */
+  const float* T;
+  const int32_t* mode;
+  const int32_t* record_len;
+  const int32_t* cav_mask;
+  double cell;
+  float ln_eps;
+  HmvitStageWeights stage[2]; /* [0] window, [1] grid */
+  const void* head_w1[2];     /* fp32 (tf32) [256][256] */
+  const float* head_b1;
+  const void* head_w2[2];
+  const float* head_b2;
+  float* xres;                /* fp32 cm [B*L][256][N]: residual stream / block output (valid slots) */
+  void* workspace;            /* hmvit_fusion_workspace_bytes() bytes */
+  float* out;                 /* fp32 [B][256][N] (head == 1) */
+} HmvitFusionArgs;
+
+size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W);
+int hmvit_fusion_forward(const HmvitFusionArgs* args, void* stream);
+/* number of kernel launches one hmvit_fusion_forward enqueues (for launch accounting) */
+int hmvit_fusion_launch_count(int32_t num_iters, int32_t head);
+
+/* ---- bring-up / self-test helpers ---------------------------------------------------------------------
+ * Writes {dynamic-smem base address & 1023, TMEM base of the first allocation} for diagnostics. */
+int hmvit_debug_probe(uint32_t* out2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMVIT_B200_H_ */

@@ -1,0 +1,92 @@
+"""CPU-side tests of the host logic and of the C-ABI library surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import hmvit_loader
+from oracle import hmvit_emul as E
+from oracle import hmvit_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    pkg = hmvit_loader.load()
+    hdr = open(os.path.join(ROOT, "include", "hmvit_b200.h")).read()
+    declared = set(re.findall(r"\b(hmvit_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(pkg._lib.EXPORTS)
+    assert os.path.exists(pkg._lib.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(pkg._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert pkg._lib.load().hmvit_abi_version() == 1
+
+
+def test_state_dict_keys_match_reference_spec():
+    pkg = hmvit_loader.load()
+    cfg = O.default_config()
+    net = pkg.HeteroFusion(cfg)
+    spec = O.state_dict_spec(cfg)
+    sd = net.state_dict()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    for k, shape in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert sd["hetero_fusion_block.window_attention.relative_position_index"].dtype == torch.int64
+    assert torch.equal(sd["hetero_fusion_block.grid_attention.relative_position_index"], O.relative_position_index(8))
+    net.load_state_dict(O.synth_state_dict(cfg, 1), strict=True)
+
+
+def test_constructor_rejects_unsupported_dims_and_cpu_input():
+    pkg = hmvit_loader.load()
+    with pytest.raises(ValueError):
+        pkg.HeteroFusion(O.default_config(input_dim=128))
+    net = pkg.HeteroFusion(O.default_config()).eval()
+    x, T, mode, rl, mask = O.synth_inputs(1, 2, 256, 8, 8, [2], 0)
+    with torch.no_grad(), pytest.raises(ValueError):
+        net(x, T, mode, rl, mask)            # CPU tensors: the product path has no CPU fallback
+
+
+def test_packed_weights_match_emulation_folding():
+    """Host-side weight folding (scale, relation_att / relation_msg) == the oracle-side folding."""
+    pkg = hmvit_loader.load()
+    cfg = O.default_config()
+    P = O.synth_state_dict(cfg, 2)
+    net = pkg.HeteroFusion(cfg)
+    net.load_state_dict(P, strict=True)
+    pk = net.hetero_fusion_block.packed()["grid"]
+    ref = E.pack_attention_weights(P, "hetero_fusion_block.grid_attention")
+    for t in (0, 1):
+        w = pk[f"wqkv{t}"].float()
+        exp = torch.cat([ref["wq"][t], ref["wk"][0][t], ref["wk"][1][t], ref["wv"][0][t], ref["wv"][1][t]], 0)
+        assert torch.equal(w, exp.to(torch.bfloat16).float())
+        assert torch.allclose(pk["bqkv"][t, :256], ref["bq"][t])
+        assert float(pk["bqkv"][t, 256:].abs().max()) == 0.0
+        for te in (0, 1):
+            assert torch.allclose(pk["bk"][te, t], ref["bk"][te][t], atol=1e-7)
+            assert torch.allclose(pk["bv"][te, t], ref["bv"][te][t], atol=1e-7)
+    # tf32 rounding keeps 10 mantissa bits
+    w1 = pk["w1_0"]
+    assert int((w1.view(torch.int32) & 0x1FFF).abs().max()) == 0
+    assert float((w1 - P["hetero_fusion_block.grid_ffd.fn.net.0.0.weight"]).abs().max()) < 1e-3
+
+
+def test_regroup_matches_oracle():
+    pkg = hmvit_loader.load()
+    dense = torch.randn(6, 3, 4, 4)
+    rl = torch.tensor([1, 3, 2])
+    a, ma = pkg.regroup(dense, rl, 4)
+    b, mb = O.regroup(dense, rl, 4)
+    assert torch.equal(a, b) and torch.equal(ma, mb) and ma.dtype == torch.int64
+
+
+def test_emulation_restructuring_is_exact():
+    """project-then-warp + folded edge weights + dead-query elimination == the reference order of ops."""
+    cfg = O.default_config()
+    P = O.synth_state_dict(cfg, 0)
+    x, T, mode, rl, mask = O.synth_inputs(2, 3, 256, 16, 16, [3, 2], seed=4, tx=8, ty=5)
+    yo = O.hetero_fusion(x, T, mode, rl, mask, P, cfg)
+    ye = E.hetero_fusion(x, T, mode, rl, mask, P, cfg)
+    assert float((ye - yo).norm() / yo.norm()) < 5e-6
