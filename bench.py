@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Benchmark of the HM-ViT fusion forward (BASELINE.json metric: fused scenes/sec, 5 agents,
+256x48x176 BEV) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on host CPU cores
+
+One "step" = one HeteroFusion forward over a batch of 8 synthetic scenes (BASELINE config 2: 5 mixed
+camera/LiDAR agents per scene, 256 x 48 x 176 BEV, window 8) per GPU.  Scenes are independent, so
+N GPUs run N x 8 scenes with no collective on the data path (weak scaling); torch.distributed is
+used only for the barrier and the max-over-ranks of the device time.
+
+JSON keys beyond the base contract: `roofline` (dominant kernel, CUDA-event time measured live in
+this run), `cpu_baseline` (the CPU oracle port timed on this host's cores on a bounded sample),
+`kernels` (per-kernel share of one step), `clocks`, `e2e`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+C, H, W, L, B_PER_GPU = 256, 48, 176, 5, 8
+N_TOK = H * W
+METRIC = "fused scenes/sec (5 agents, 256x48x176 BEV)"
+WORKLOAD = ("BASELINE config 2: HM-ViT fusion forward, 5 mixed-modality agents (camera p=0.5, ego mixed), "
+            "batch 8 scenes per GPU, 256x48x176 BEV, window 8, num_iters 2")
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic work (stated in DESIGN.md)
+# ---------------------------------------------------------------------------------------------
+def stage_flops(Lv, n_q_agents):
+    """FLOPs of one (window|grid) stage of one scene: projections for all Lv agents (3 x 2C^2 per
+    token: Q, K, V), attention + output projection + FFN for n_q_agents query agents."""
+    S = 64
+    qkv = 3 * Lv * N_TOK * 2 * C * C
+    attn = 2 * n_q_agents * N_TOK * (Lv * S) * 2 * C
+    oproj = n_q_agents * N_TOK * 2 * C * C
+    ffn = n_q_agents * N_TOK * 4 * C * C
+    return {"qkv": qkv, "attn": attn, "out": oproj, "ffn": ffn}
+
+
+def scene_flops(Lv, num_iters=2):
+    tot = 0
+    for _ in range(2 * num_iters):
+        tot += sum(stage_flops(Lv, Lv).values())
+    return tot + N_TOK * 4 * C * C            # + head
+
+
+# ---------------------------------------------------------------------------------------------
+def sample_clocks(stop, out, gpu_index):
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            parts = [p.strip() for p in r.stdout.strip().split(",")]
+            if len(parts) >= 6:
+                out.append(parts)
+        except Exception:  # noqa: BLE001
+            pass
+        stop.wait(0.2)
+
+
+def clocks_summary(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+    sm = [float(s[0]) for s in samples if s[0].replace(".", "").isdigit()]
+    mx = [float(s[1]) for s in samples if s[1].replace(".", "").isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+# ---------------------------------------------------------------------------------------------
+def make_inputs(seed, batch, record_len=None):
+    from oracle import hmvit_oracle as O
+    rl = record_len if record_len is not None else [L] * batch
+    return O.synth_inputs(batch, L, C, H, W, rl, seed)
+
+
+def cpu_baseline(steps=2, warmup=1):
+    """The CPU oracle port (same algorithm as the reference, vectorised PyTorch fp32) on this host's
+    cores: one config-2 scene per step."""
+    from oracle import hmvit_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.default_config()
+    P = O.synth_state_dict(cfg, 0)
+    x, T, mode, rl, mask = make_inputs(1234 + 2, 1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.hetero_fusion(x, T, mode, rl, mask, P, cfg)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    dt = statistics.median(times)
+    return {"value": 1.0 / dt, "unit": "scenes/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} timed + {warmup} warm-up forwards of ONE config-2 scene (5 agents, 256x48x176), "
+                      f"oracle/hmvit_oracle.py, torch fp32, {cores} threads; median {dt:.2f} s/scene"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    cb = cpu_baseline(steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "scenes/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU cores (oracle port; the Python "
+                       "reference cannot travel to the GPU box); each step = one scene of the workload"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+def kernel_breakdown(pkg, net, inp, iters=3):
+    """Per-kernel CUDA-event times of one forward, issued op by op through the same C-ABI entry points
+    and in the same order as hmvit_fusion_forward."""
+    lib, ops = pkg._lib, pkg.ops
+    x, T, mode, rl, cav = inp
+    Bq = x.shape[0]
+    dev = x.device
+    blk = net.hetero_fusion_block
+    pk, hp = blk.packed(), net.head_packed()
+    rows = Bq * L * N_TOK
+    qkv = torch.empty(5, rows, C, dtype=torch.bfloat16, device=dev)
+    att = torch.empty(rows, C, dtype=torch.bfloat16, device=dev)
+    hid = torch.empty(Bq, L, C, N_TOK, device=dev)
+    xres = torch.empty_like(x)
+    out = torch.empty(Bq, C, N_TOK, device=dev)
+    cell = float(blk.discrete_ratio) * float(blk.downsample_rate)
+    common = dict(B=Bq, L=L, N=N_TOK, mode=mode, record_len=rl)
+    acc = {}
+
+    def timed(name, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        acc.setdefault(name, []).append((e0, e1))
+
+    for _ in range(iters):
+        for it in range(net.num_iters):
+            for kind, kname in ((0, "window"), (1, "grid")):
+                w = pk[kname]
+                dead = net.skip_dead_queries and it == net.num_iters - 1 and kind == 1
+                xsrc = x if (it == 0 and kind == 0) else xres
+                timed("ln_qkv_gemm", lambda: ops.rowgemm(lib.GEMM_QKV, n_out=1280, a=xsrc, w0=w["wqkv0"], w1=w["wqkv1"],
+                                                         bias=w["bqkv"], out=qkv, ln_gamma=w["ln1_g"], ln_beta=w["ln1_b"],
+                                                         ego_only=dead, **common))
+                timed("group_attn", lambda: ops.group_attn(B=Bq, L=L, H=H, W=W, kind=kind, mode=mode, record_len=rl,
+                                                           cav_mask=cav, T=T, cell=cell, q=qkv[0], k=qkv[1:3], v=qkv[3:5],
+                                                           bk=w["bk"], bv=w["bv"], bias_table=w["bias_table"], out=att,
+                                                           ego_only=dead))
+                timed("out_gemm", lambda: ops.rowgemm(lib.GEMM_OUT, n_out=256, a=att, w0=w["wa0"], w1=w["wa1"], bias=w["ba"],
+                                                      out=xres, resid=xsrc, ego_only=dead, **common))
+                timed("ffn1_gemm", lambda: ops.rowgemm(lib.GEMM_FFN1, n_out=256, a=xres, w0=w["w1_0"], w1=w["w1_1"],
+                                                       bias=w["b1"], out=hid, ln_gamma=w["ln2_g"], ln_beta=w["ln2_b"],
+                                                       ego_only=dead, **common))
+                timed("ffn2_gemm", lambda: ops.rowgemm(lib.GEMM_FFN2, n_out=256, a=hid, w0=w["w2_0"], w1=w["w2_1"],
+                                                       bias=w["b2"], out=xres, resid=xres, ego_only=dead, **common))
+        timed("head_gemm", lambda: ops.rowgemm(lib.GEMM_HEAD1, n_out=256, a=xres, w0=hp["w1_0"], w1=hp["w1_1"], bias=hp["b1"],
+                                               out=hid, **common))
+        timed("head_gemm", lambda: ops.rowgemm(lib.GEMM_HEAD2, n_out=256, a=hid, w0=hp["w2_0"], w1=hp["w2_1"], bias=hp["b2"],
+                                               out=out, **common))
+    torch.cuda.synchronize()
+    res = {}
+    for name, evs in acc.items():
+        ms = [a.elapsed_time(b) for a, b in evs]
+        res[name] = {"launches_per_step": len(ms) // iters, "ms_per_step": sum(ms) / iters, "ms_per_launch": sum(ms) / len(ms)}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="scenes per GPU per step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    import hmvit_loader
+    from oracle import hmvit_oracle as O
+    pkg = hmvit_loader.load()
+    cfg = O.default_config()
+    net = pkg.HeteroFusion(cfg).eval()
+    net.load_state_dict(O.synth_state_dict(cfg, 0), strict=True)
+    net = net.to(dev)
+    Bq = args.batch
+    x, T, mode, rl, mask = make_inputs(1234 + 2 + 1000 * rank, Bq)
+    host = [x.pin_memory(), T.pin_memory(), mode.pin_memory(), rl.to(torch.int32).pin_memory(), mask.to(torch.int32).pin_memory()]
+    dev_in = [t.to(dev) for t in host]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput ----------------
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            net(*dev_in)
+        samples, stop = [], threading.Event()
+        th = threading.Thread(target=sample_clocks, args=(stop, samples, local_rank), daemon=True)
+        th.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            net(*dev_in)
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        # ---------------- end to end: pinned host -> device -> forward -> host ----------------
+        out_host = torch.empty(Bq, C, H, W).pin_memory()
+        stage = [torch.empty_like(t, device=dev) for t in host]
+        for _ in range(2):
+            for s, h in zip(stage, host):
+                s.copy_(h, non_blocking=True)
+            out_host.copy_(net(*stage), non_blocking=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            for s, h in zip(stage, host):
+                s.copy_(h, non_blocking=True)
+            out_host.copy_(net(*stage), non_blocking=True)
+        f1.record()
+        barrier()
+        ms_e2e = f0.elapsed_time(f1)
+        stop.set()
+        th.join(timeout=2)
+        kern = kernel_breakdown(pkg, net, dev_in) if rank == 0 else None
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    scenes = Bq * world * args.steps
+    value = scenes / (ms_total / 1e3)
+    e2e_value = scenes / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = out_host.numel() * out_host.element_size()
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        pk = json.load(open(peaks_path))
+        hbm, tf_sus, tf_burst, src = pk["hbm_gbs"], pk["bf16_tflops_sustained"], pk["bf16_tflops"], "measured (MEASURED_PEAKS.json)"
+    else:
+        hbm, tf_sus, tf_burst, src = 6650.0, 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+    # dominant kernel = largest share of the step
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    Lv = L
+    launches = kern[dom]["launches_per_step"]
+    if dom == "group_attn":
+        # algorithmic bytes per launch: read Q, K', V' once and write O, bf16 rows, every valid agent of
+        # every scene (the last launch of a step serves ego queries only; averaged over the 4 launches)
+        per_full = 4 * Lv * N_TOK * C * 2 * Bq
+        per_dead = (2 * Lv + 2) * N_TOK * C * 2 * Bq
+        alg = (per_full * (launches - 1) + per_dead) / launches if net.skip_dead_queries else per_full
+        achieved = alg / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
+        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                "traffic": None, "peak_source": src,
+                "note": "algorithmic bytes = Q + K' + V' read once + O written, bf16 (DESIGN.md); the kernel is "
+                        "gather (L2->SM) bound, its tensor work is 2*2*Lv*N*(Lv*64)*2C FLOP per scene"}
+    else:
+        fl = {"ln_qkv_gemm": "qkv", "out_gemm": "out", "ffn1_gemm": "ffn", "ffn2_gemm": "ffn", "head_gemm": "ffn"}[dom]
+        f = stage_flops(Lv, Lv)[fl] * Bq * (0.5 if fl == "ffn" else 1.0)
+        achieved = f / (kern[dom]["ms_per_launch"] * 1e-3) / 1e12
+        roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
+                "frac": achieved / tf_sus, "traffic": None, "peak_source": src}
+
+    total_kernel_ms = sum(v["ms_per_step"] for v in kern.values())
+    whole_flops = scene_flops(Lv) * Bq * world
+    line = {
+        "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (projections, attention) + tf32 (FFN), fp32 accumulate and residual stream",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "scenes_per_gpu_per_step": Bq, "agents": L, "bev": [C, H, W],
+                   "l2": "inputs per step (346 MB fp32 features + 1.7 GB workspace) exceed the 126 MB L2; no explicit flush",
+                   "timing": "CUDA events on the launch stream, barrier + synchronize both sides, max over ranks"},
+        "clocks": clocks_summary(samples),
+        "e2e": {"value": e2e_value, "unit": "scenes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": pkg.ops.fusion_launch_count(net.num_iters, True) * args.steps,
+        "roofline": roof,
+        "whole_forward": {"algorithmic_gflop_per_scene": scene_flops(Lv) / 1e9,
+                          "achieved_tflops": whole_flops / (ms_total / args.steps * 1e-3) / 1e12,
+                          "frac_of_sustained_bf16_peak": whole_flops / (ms_total / args.steps * 1e-3) / 1e12 / (tf_sus * world),
+                          "peak_source": src},
+        "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"],
+                        "share": round(v["ms_per_step"] / total_kernel_ms, 4)} for k, v in kern.items()},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(2, 1)
+    elif world == 1:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,7 +56,7 @@ struct RowGemmCfg {
   static constexpr int CHUNK_BYTES = BM * 128;             // 16 KB: 128 rows x 128 B of K
   static constexpr int K_PER_CHUNK = 128 / ES;             // 64 bf16 / 32 tf32
   static constexpr int NCHA = K * ES / 128;                // A chunks: 4 (bf16) / 8 (tf32)
-  static constexpr int NS = (ES == 2) ? 3 : 4;             // B stages
+  static constexpr int NS = (ES == 2) ? 2 : 4;             // B stages (bf16: 2 so that two CTAs fit one SM)
   static constexpr int A_BYTES = NCHA * CHUNK_BYTES;
   static constexpr int B_BYTES = NS * CHUNK_BYTES;
   static constexpr int BAR_BYTES = 256;
@@ -143,10 +143,13 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         // shifted single pass statistics (shift = first channel) -- biased variance like nn.LayerNorm
         const float s0 = valid ? __ldg(src) : 0.f;
         float sum = 0.f, sq = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < kC; ++c) {
-          const float d = (valid ? __ldg(src + static_cast<size_t>(c) * p.N) : 0.f) - s0;
-          sum += d; sq += d * d;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kC; c0 += 32) {
+          float xv[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { const float d = xv[e] - s0; sum += d; sq += d * d; }
         }
         const float md = sum * (1.0f / kC);
         mean = s0 + md;
@@ -156,25 +159,30 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       const float* gam = p.ln_gamma + type * kC;
       const float* bet = p.ln_beta + type * kC;
       constexpr int EPU = 16 / ES;                      // elements per 16-byte unit
-#pragma unroll 2
-      for (int u = 0; u < kC / EPU; ++u) {
-        float v[EPU];
+      constexpr int UPB = 32 / EPU;                     // units per batch of 32 channels
+#pragma unroll 1
+      for (int c0 = 0; c0 < kC; c0 += 32) {
+        float xv[32];
 #pragma unroll
-        for (int e = 0; e < EPU; ++e) {
-          const int c = u * EPU + e;
-          float x = valid ? __ldg(src + static_cast<size_t>(c) * p.N) : 0.f;
-          if constexpr (PRO == PRO_CM_LN) x = valid ? ((x - mean) * rstd * __ldg(gam + c) + __ldg(bet + c)) : 0.f;
-          v[e] = x;
+        for (int e = 0; e < 32; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+        if constexpr (PRO == PRO_CM_LN) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) xv[e] = valid ? ((xv[e] - mean) * rstd * __ldg(gam + c0 + e) + __ldg(bet + c0 + e)) : 0.f;
         }
-        uint4 pk;
-        if constexpr (ES == 2) {
-          pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
-          pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-        } else {
-          pk.x = __float_as_uint(tf32_rn(v[0])); pk.y = __float_as_uint(tf32_rn(v[1]));
-          pk.z = __float_as_uint(tf32_rn(v[2])); pk.w = __float_as_uint(tf32_rn(v[3]));
+#pragma unroll
+        for (int uu = 0; uu < UPB; ++uu) {
+          const float* v = xv + uu * EPU;
+          const int u = c0 / EPU + uu;
+          uint4 pk;
+          if constexpr (ES == 2) {
+            pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+            pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+          } else {
+            pk.x = __float_as_uint(tf32_rn(v[0])); pk.y = __float_as_uint(tf32_rn(v[1]));
+            pk.z = __float_as_uint(tf32_rn(v[2])); pk.w = __float_as_uint(tf32_rn(v[3]));
+          }
+          *reinterpret_cast<uint4*>(sA + (u >> 3) * Cfg::CHUNK_BYTES + sw128_offset(row, u & 7)) = pk;
         }
-        *reinterpret_cast<uint4*>(sA + (u >> 3) * Cfg::CHUNK_BYTES + sw128_offset(row, u & 7)) = pk;
       }
     }
     fence_proxy_async_smem();
@@ -218,10 +226,12 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             float* dst = p.out_cm + (static_cast<size_t>(b) * p.out_L + lo) * kC * p.N + static_cast<size_t>(n0) * p.N + tok;
             const float* res = nullptr;
             if constexpr (EPI == EPI_CM_RESID) res = p.resid_cm + static_cast<size_t>(a) * kC * p.N + static_cast<size_t>(n0) * p.N + tok;
+            float rv[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) rv[k] = (EPI == EPI_CM_RESID) ? res[static_cast<size_t>(k) * p.N] : 0.f;
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-              float v = __uint_as_float(r[k]) + __ldg(bias + k);
-              if constexpr (EPI == EPI_CM_RESID) v += res[static_cast<size_t>(k) * p.N];
+              float v = __uint_as_float(r[k]) + __ldg(bias + k) + rv[k];
               if constexpr (EPI == EPI_CM_GELU) v = tf32_rn(gelu_erf(v));
               dst[static_cast<size_t>(k) * p.N] = v;
             }
