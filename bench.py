@@ -167,13 +167,10 @@ def kernel_breakdown(pkg, net, inp, iters=3):
                                                            cav_mask=cav, T=T, cell=cell, q=qkv[0], k=qkv[1:3], v=qkv[3:5],
                                                            bk=w["bk"], bv=w["bv"], bias_table=w["bias_table"], out=att,
                                                            ego_only=dead))
-                timed("out_gemm", lambda: ops.rowgemm(lib.GEMM_OUT, n_out=256, a=att, w0=w["wa0"], w1=w["wa1"], bias=w["ba"],
-                                                      out=xres, resid=xsrc, ego_only=dead, **common))
-                timed("ffn1_gemm", lambda: ops.rowgemm(lib.GEMM_FFN1, n_out=256, a=xres, w0=w["w1_0"], w1=w["w1_1"],
-                                                       bias=w["b1"], out=hid, ln_gamma=w["ln2_g"], ln_beta=w["ln2_b"],
-                                                       ego_only=dead, **common))
-                timed("ffn2_gemm", lambda: ops.rowgemm(lib.GEMM_FFN2, n_out=256, a=hid, w0=w["w2_0"], w1=w["w2_1"],
-                                                       bias=w["b2"], out=xres, resid=xres, ego_only=dead, **common))
+                timed("out_ffn_chain", lambda: ops.out_ffn_chain(o=att, resid=xsrc, out=xres, wa0=w["wa0"], wa1=w["wa1"], ba=w["ba"],
+                                                                 ln_gamma=w["ln2_g"], ln_beta=w["ln2_b"], w1_0=w["w1_0"],
+                                                                 w1_1=w["w1_1"], b1=w["b1"], w2_0=w["w2_0"], w2_1=w["w2_1"],
+                                                                 b2=w["b2"], ego_only=dead, **common))
         timed("head_gemm", lambda: ops.rowgemm(lib.GEMM_HEAD1, n_out=256, a=xres, w0=hp["w1_0"], w1=hp["w1_1"], bias=hp["b1"],
                                                out=hid, **common))
         timed("head_gemm", lambda: ops.rowgemm(lib.GEMM_HEAD2, n_out=256, a=hid, w0=hp["w2_0"], w1=hp["w2_1"], bias=hp["b2"],
@@ -305,8 +302,8 @@ def main():
                 "note": "algorithmic bytes = Q + K' + V' read once + O written, bf16 (DESIGN.md); the kernel is "
                         "gather (L2->SM) bound, its tensor work is 2*2*Lv*N*(Lv*64)*2C FLOP per scene"}
     else:
-        fl = {"ln_qkv_gemm": "qkv", "out_gemm": "out", "ffn1_gemm": "ffn", "ffn2_gemm": "ffn", "head_gemm": "ffn"}[dom]
-        f = stage_flops(Lv, Lv)[fl] * Bq * (0.5 if fl == "ffn" else 1.0)
+        sf = stage_flops(Lv, Lv)
+        f = {"ln_qkv_gemm": sf["qkv"], "out_ffn_chain": sf["out"] + sf["ffn"], "head_gemm": sf["ffn"] / Lv / 2}[dom] * Bq
         achieved = f / (kern[dom]["ms_per_launch"] * 1e-3) / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
                 "frac": achieved / tf_sus, "traffic": None, "peak_source": src}

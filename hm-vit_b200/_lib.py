@@ -14,7 +14,7 @@ GEMM_QKV, GEMM_OUT, GEMM_FFN1, GEMM_FFN2, GEMM_HEAD1, GEMM_HEAD2, GEMM_QKV_NOLN 
 EXPORTS = (
     "hmvit_abi_version", "hmvit_last_error", "hmvit_rowgemm", "hmvit_group_attn", "hmvit_warp_bilinear",
     "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
-    "hmvit_debug_probe",
+    "hmvit_debug_probe", "hmvit_out_ffn_chain",
 )
 
 
@@ -24,6 +24,13 @@ class RowGemmArgs(C.Structure):
                 ("a", C.c_void_p), ("w", C.c_void_p * 2), ("bias", C.c_void_p),
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float),
                 ("resid", C.c_void_p), ("out", C.c_void_p)]
+
+
+class ChainArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("N", C.c_int32), ("mode", C.c_void_p), ("record_len", C.c_void_p),
+                ("ego_only", C.c_int32), ("o", C.c_void_p), ("resid", C.c_void_p), ("out", C.c_void_p),
+                ("wa", C.c_void_p * 2), ("ba", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
+                ("ln_eps", C.c_float), ("w1", C.c_void_p * 2), ("b1", C.c_void_p), ("w2", C.c_void_p * 2), ("b2", C.c_void_p)]
 
 
 class AttnArgs(C.Structure):
@@ -45,7 +52,7 @@ class StageWeights(C.Structure):
 
 class FusionArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("num_iters", C.c_int32), ("head", C.c_int32), ("skip_dead", C.c_int32),
+                ("num_iters", C.c_int32), ("head", C.c_int32), ("skip_dead", C.c_int32), ("unfused", C.c_int32),
                 ("x", C.c_void_p), ("T", C.c_void_p), ("mode", C.c_void_p), ("record_len", C.c_void_p),
                 ("cav_mask", C.c_void_p), ("cell", C.c_double), ("ln_eps", C.c_float),
                 ("stage", StageWeights * 2),
@@ -70,6 +77,8 @@ def load():
     lib.hmvit_last_error.restype = C.c_char_p
     lib.hmvit_rowgemm.argtypes = [C.c_int, C.POINTER(RowGemmArgs), C.c_void_p]
     lib.hmvit_rowgemm.restype = C.c_int
+    lib.hmvit_out_ffn_chain.argtypes = [C.POINTER(ChainArgs), C.c_void_p]
+    lib.hmvit_out_ffn_chain.restype = C.c_int
     lib.hmvit_group_attn.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     lib.hmvit_group_attn.restype = C.c_int
     lib.hmvit_warp_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

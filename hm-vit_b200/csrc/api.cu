@@ -3,6 +3,7 @@
 #include "../../include/hmvit_b200.h"
 #include "rowgemm.cuh"
 #include "attn.cuh"
+#include "chain.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -37,7 +38,7 @@ static void load_encode() {
       qres == cudaDriverEntryPointSuccess)
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
 }
-static int make_weight_tmap(CUtensorMap* map, const void* w, int n_out, int es) {
+static int make_weight_tmap(CUtensorMap* map, const void* w, long long n_out, int es) {
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) return fail(HMVIT_ERR_CUDA, "hmvit: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(n_out)};
@@ -125,6 +126,50 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
     default:
       return fail(HMVIT_ERR_ARG, "hmvit: rowgemm: unknown variant");
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused output projection + FFN chain
+// ------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
+  HMVIT_CHECK_ARG(a != nullptr, "chain: null args");
+  HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->N > 0, "chain: B, L, N must be positive");
+  HMVIT_CHECK_ARG(a->mode && a->record_len && a->o && a->resid && a->out && a->wa[0] && a->wa[1] && a->ba && a->ln_gamma &&
+                  a->ln_beta && a->w1[0] && a->w1[1] && a->b1 && a->w2[0] && a->w2[1] && a->b2, "chain: null pointer");
+  ChainMaps maps;
+  int rc = make_weight_tmap(&maps.o, a->o, static_cast<long long>(a->B) * a->L * a->N, 2); if (rc) return rc;
+  for (int t = 0; t < 2; ++t) {
+    rc = make_weight_tmap(&maps.wa[t], a->wa[t], 256, 2); if (rc) return rc;
+    rc = make_weight_tmap(&maps.w1[t], a->w1[t], 256, 4); if (rc) return rc;
+    rc = make_weight_tmap(&maps.w2[t], a->w2[t], 256, 4); if (rc) return rc;
+  }
+  ChainParams p;
+  p.B = a->B; p.L = a->L; p.N = a->N; p.mode = a->mode; p.record_len = a->record_len; p.tile_ego_only = a->ego_only ? 1 : 0;
+  p.resid_cm = a->resid; p.out_cm = a->out; p.ba = a->ba; p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_eps = a->ln_eps;
+  p.b1 = a->b1; p.b2 = a->b2;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  const long long tiles = static_cast<long long>(a->B) * a->L * ((a->N + ChainCfg::BM - 1) / ChainCfg::BM);
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  chain_kernel<<<grid, ChainCfg::THREADS, ChainCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(maps, p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,7 +283,7 @@ extern "C" size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, 
   return bytes;
 }
 
-extern "C" int hmvit_fusion_launch_count(int32_t num_iters, int32_t head) { return num_iters * 2 * 5 + (head ? 2 : 0); }
+extern "C" int hmvit_fusion_launch_count(int32_t num_iters, int32_t head) { return num_iters * 2 * 3 + (head ? 2 : 0); }
 
 extern "C" int hmvit_fusion_forward(const HmvitFusionArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a != nullptr, "fusion_forward: null args");
@@ -277,14 +322,25 @@ extern "C" int hmvit_fusion_forward(const HmvitFusionArgs* a, void* stream) {
       t.q = qkv; t.k = qkv + rows * 256; t.v = qkv + rows * 256 * 3; t.bk = w.bk; t.bv = w.bv; t.bias_table = w.bias_table;
       t.out = att;
       rc = hmvit_group_attn(&t, stream); if (rc) return rc;
-      // output projection + residual
-      g.n_out = 256; g.a = att; g.w[0] = w.wa[0]; g.w[1] = w.wa[1]; g.bias = w.ba; g.resid = xsrc; g.out = a->xres;
-      rc = hmvit_rowgemm(HMVIT_GEMM_OUT, &g, stream); if (rc) return rc;
-      // pre-norm feed-forward + residual
-      g.a = a->xres; g.w[0] = w.w1[0]; g.w[1] = w.w1[1]; g.bias = w.b1; g.ln_gamma = w.ln2_g; g.ln_beta = w.ln2_b; g.out = hid;
-      rc = hmvit_rowgemm(HMVIT_GEMM_FFN1, &g, stream); if (rc) return rc;
-      g.a = hid; g.w[0] = w.w2[0]; g.w[1] = w.w2[1]; g.bias = w.b2; g.resid = a->xres; g.out = a->xres;
-      rc = hmvit_rowgemm(HMVIT_GEMM_FFN2, &g, stream); if (rc) return rc;
+      if (a->unfused) {
+        // output projection + residual
+        g.n_out = 256; g.a = att; g.w[0] = w.wa[0]; g.w[1] = w.wa[1]; g.bias = w.ba; g.resid = xsrc; g.out = a->xres;
+        rc = hmvit_rowgemm(HMVIT_GEMM_OUT, &g, stream); if (rc) return rc;
+        // pre-norm feed-forward + residual
+        g.a = a->xres; g.w[0] = w.w1[0]; g.w[1] = w.w1[1]; g.bias = w.b1; g.ln_gamma = w.ln2_g; g.ln_beta = w.ln2_b; g.out = hid;
+        rc = hmvit_rowgemm(HMVIT_GEMM_FFN1, &g, stream); if (rc) return rc;
+        g.a = hid; g.w[0] = w.w2[0]; g.w[1] = w.w2[1]; g.bias = w.b2; g.resid = a->xres; g.out = a->xres;
+        rc = hmvit_rowgemm(HMVIT_GEMM_FFN2, &g, stream); if (rc) return rc;
+      } else {
+        // output projection + residual + pre-norm feed-forward + residual, one kernel
+        HmvitChainArgs c;
+        memset(&c, 0, sizeof(c));
+        c.B = a->B; c.L = a->L; c.N = N; c.mode = a->mode; c.record_len = a->record_len; c.ego_only = dead;
+        c.o = att; c.resid = xsrc; c.out = a->xres;
+        c.wa[0] = w.wa[0]; c.wa[1] = w.wa[1]; c.ba = w.ba; c.ln_gamma = w.ln2_g; c.ln_beta = w.ln2_b; c.ln_eps = a->ln_eps;
+        c.w1[0] = w.w1[0]; c.w1[1] = w.w1[1]; c.b1 = w.b1; c.w2[0] = w.w2[0]; c.w2[1] = w.w2[1]; c.b2 = w.b2;
+        rc = hmvit_out_ffn_chain(&c, stream); if (rc) return rc;
+      }
     }
   }
   if (a->head) {

@@ -383,6 +383,7 @@ def _run_fusion(block: HeteroFusionBlock, fusion, x, pairwise_t_matrix, mode, re
     args.B, args.L, args.H, args.W = B, L, H, W
     args.num_iters, args.head = num_iters, 1 if head else 0
     args.skip_dead = 1 if (head and fusion.skip_dead_queries) else 0
+    args.unfused = 1 if getattr(block, "unfused_chain", False) else 0
     args.x, args.T = x.data_ptr(), T.data_ptr()
     args.mode, args.record_len, args.cav_mask = mode_i.data_ptr(), rl.data_ptr(), cav.data_ptr()
     args.cell = float(block.discrete_ratio) * float(block.downsample_rate)

@@ -49,6 +49,21 @@ def rowgemm(variant, *, B, L, N, n_out, mode, record_len, a, w0, w1, bias, out, 
     return out
 
 
+def out_ffn_chain(*, B, L, N, mode, record_len, o, resid, out, wa0, wa1, ba, ln_gamma, ln_beta, w1_0, w1_1, b1, w2_0, w2_1, b2,
+                  ego_only=False, ln_eps=1e-5):
+    args = _lib.ChainArgs()
+    args.B, args.L, args.N = B, L, N
+    args.mode, args.record_len = mode.data_ptr(), record_len.data_ptr()
+    args.ego_only = 1 if ego_only else 0
+    args.o, args.resid, args.out = o.data_ptr(), resid.data_ptr(), out.data_ptr()
+    args.wa[0], args.wa[1] = wa0.data_ptr(), wa1.data_ptr()
+    args.ba, args.ln_gamma, args.ln_beta, args.ln_eps = ba.data_ptr(), ln_gamma.data_ptr(), ln_beta.data_ptr(), ln_eps
+    args.w1[0], args.w1[1], args.b1 = w1_0.data_ptr(), w1_1.data_ptr(), b1.data_ptr()
+    args.w2[0], args.w2[1], args.b2 = w2_0.data_ptr(), w2_1.data_ptr(), b2.data_ptr()
+    _lib.check(_lib.load().hmvit_out_ffn_chain(C.byref(args), _stream()))
+    return out
+
+
 def group_attn(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, k, v, bk, bv, bias_table, out,
                ego_only=False, key_mask=None):
     args = _lib.AttnArgs()

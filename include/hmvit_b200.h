@@ -75,6 +75,32 @@ typedef struct {
 
 int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* args, void* stream);
 
+/* ---- fused output projection + residual + pre-norm FFN + residual --------------------------------------
+ * One kernel for  x' = x + O W_a^T + b_a ;  x'' = x' + W_2 gelu(W_1 LN_type(x') + b_1) + b_2 , i.e.
+ *   HeteroAttention.to_out + residual   opencood/models/sub_modules/hetero_fusion.py:142-152, 399, 442
+ *   HeteroPreNormResidual(HeteroFeedForward)   opencood/models/base_transformer.py:129-136, 180-192
+ * (same arithmetic as HMVIT_GEMM_OUT -> FFN1 -> FFN2, intermediates kept in TMEM / shared memory). */
+typedef struct {
+  int32_t B, L, N;
+  const int32_t* mode;
+  const int32_t* record_len;
+  int32_t ego_only;           /* process slot 0 tiles only */
+  const void* o;              /* attention output, bf16 rows [B*L*N][256] */
+  const float* resid;         /* x, fp32 cm [B*L][256][N] */
+  float* out;                 /* x'', fp32 cm [B*L][256][N]; may be the same buffer as resid */
+  const void* wa[2];          /* bf16 [256][256] per type */
+  const float* ba;            /* [2][256] */
+  const float* ln_gamma;      /* [2][256] */
+  const float* ln_beta;       /* [2][256] */
+  float ln_eps;
+  const void* w1[2];          /* fp32 (tf32) [256][256] */
+  const float* b1;            /* [2][256] */
+  const void* w2[2];          /* fp32 (tf32) [256][256] */
+  const float* b2;            /* [2][256] */
+} HmvitChainArgs;
+
+int hmvit_out_ffn_chain(const HmvitChainArgs* args, void* stream);
+
 /* ---- fused warp + mask + multi-agent window / grid attention ---------------------------------------
  * Replaces HeteroFusionBlock.warp_features + the ego loop around HeteroAttention.forward
  *   opencood/models/sub_modules/hetero_fusion.py:338-361, 373-397 (window) / 412-440 (grid), 187-277
@@ -136,6 +162,7 @@ typedef struct {
   int32_t num_iters;          /* block applications (weights shared) */
   int32_t head;               /* 1: ego slice + mlp_head -> out [B][256][N]; 0: stop after the blocks */
   int32_t skip_dead;          /* 1 (with head): last grid stage computes ego-0 queries only (exact) */
+  int32_t unfused;            /* 1: run OUT / FFN1 / FFN2 as three row-GEMMs instead of the fused chain kernel */
   const float* x;             /* fp32 cm [B*L][256][N], not modified */
   const float* T;
   const int32_t* mode;

@@ -162,6 +162,60 @@ def check_rowgemm(variant_name, N=200, seed=3):
     return res
 
 
+def check_chain(N=200, ego_only=False, seed=9):
+    """Fused OUT+FFN chain kernel against a torch-CPU evaluation with the same operand rounding and
+    against the three-kernel row-GEMM sequence."""
+    p = pkg()
+    lib = p._lib
+    B, L, C = 2, 3, 256
+    g = torch.Generator().manual_seed(seed)
+    record_len = torch.tensor([3, 2], dtype=torch.int32)
+    mode = torch.tensor([[1, 0, 1], [0, 1, 0]], dtype=torch.int32)
+    o = torch.randn(B * L * N, C, generator=g).to(torch.bfloat16)
+    x = torch.randn(B, L, C, N, generator=g) * 1.3 + 0.2
+    gam = 1 + 0.1 * torch.randn(2, C, generator=g)
+    bet = 0.1 * torch.randn(2, C, generator=g)
+    wa = torch.randn(2, C, C, generator=g) / 16
+    w1 = torch.randn(2, C, C, generator=g) / 16
+    w2 = torch.randn(2, C, C, generator=g) / 16
+    ba, b1, b2 = (0.1 * torch.randn(2, C, generator=g) for _ in range(3))
+    d = lambda t: t.to(DEV).contiguous()
+    wa_d = [d(wa[t].to(torch.bfloat16)) for t in range(2)]
+    w1_d = [d(tf32(w1[t])) for t in range(2)]
+    w2_d = [d(tf32(w2[t])) for t in range(2)]
+    common = dict(B=B, L=L, N=N, mode=d(mode), record_len=d(record_len))
+    out = torch.full((B, L, C, N), float("nan"), device=DEV)
+    p.ops.out_ffn_chain(o=d(o), resid=d(x), out=out, wa0=wa_d[0], wa1=wa_d[1], ba=d(ba), ln_gamma=d(gam), ln_beta=d(bet),
+                        w1_0=w1_d[0], w1_1=w1_d[1], b1=d(b1), w2_0=w2_d[0], w2_1=w2_d[1], b2=d(b2), ego_only=ego_only, **common)
+    torch.cuda.synchronize()
+    # the same arithmetic as three row-GEMM launches
+    x1 = torch.full((B, L, C, N), float("nan"), device=DEV)
+    hid = torch.full((B, L, C, N), float("nan"), device=DEV)
+    p.ops.rowgemm(lib.GEMM_OUT, n_out=256, a=d(o), w0=wa_d[0], w1=wa_d[1], bias=d(ba), out=x1, resid=d(x), ego_only=ego_only, **common)
+    p.ops.rowgemm(lib.GEMM_FFN1, n_out=256, a=x1, w0=w1_d[0], w1=w1_d[1], bias=d(b1), out=hid, ln_gamma=d(gam), ln_beta=d(bet),
+                  ego_only=ego_only, **common)
+    p.ops.rowgemm(lib.GEMM_FFN2, n_out=256, a=hid, w0=w2_d[0], w1=w2_d[1], bias=d(b2), out=x1, resid=x1, ego_only=ego_only, **common)
+    torch.cuda.synchronize()
+    out, x1 = out.cpu(), x1.cpu()
+    worst, worst_seq = 0.0, 0.0
+    for b in range(B):
+        for l in range(L):
+            need = l < int(record_len[b]) and (not ego_only or l == 0)
+            if not need:
+                assert torch.isnan(out[b, l]).all(), f"(b={b}, l={l}) must not be written"
+                continue
+            t = int(mode[b, l])
+            xp = o.float().view(B, L, N, C)[b, l] @ bf16(wa[t]).t() + ba[t] + x[b, l].t()
+            h = tf32(F.gelu(tf32(F.layer_norm(xp, (C,), gam[t], bet[t], 1e-5)) @ tf32(w1[t]).t() + b1[t]))
+            exp = xp + h @ tf32(w2[t]).t() + b2[t]
+            assert torch.isfinite(out[b, l]).all()
+            worst = max(worst, rel_l2(out[b, l].t(), exp))
+            worst_seq = max(worst_seq, rel_l2(out[b, l], x1[b, l]))
+    res = {"rel_l2_vs_cpu": worst, "rel_l2_vs_rowgemm_sequence": worst_seq}
+    assert worst < 2e-4 and worst_seq < 2e-5, res
+    return res
+
+
 # ----------------------------------------------------------------------------------------------
 def check_warp_mask_golden():
     """Stand-alone warp and ROI mask against the reference's own outputs (tests/golden/warp_mask.npz)."""
@@ -378,6 +432,8 @@ CHECKS = {
     "gemm_head1": lambda: check_rowgemm("HEAD1"),
     "gemm_head2": lambda: check_rowgemm("HEAD2"),
     "gemm_qkv_n8448": lambda: check_rowgemm("QKV", N=8448 // 8),
+    "chain": check_chain,
+    "chain_ego_n1056": lambda: check_chain(N=1056, ego_only=True),
     "warp_mask_golden": check_warp_mask_golden,
     "mask_adversarial": check_mask_adversarial,
     "attention_golden": check_attention_golden,
