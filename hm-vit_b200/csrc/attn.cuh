@@ -6,10 +6,10 @@
 //   1. evaluates the j->i source-pixel map for the group's 64 tokens (fp64, like the oracle), the
 //      nearest-neighbour ROI visibility (bit-exact key mask) and the 4 bilinear taps;
 //   2. gathers the PROJECTED keys / values of agent j (edge-type weights already folded into the
-//      projection) with 16-byte vector loads, blends the taps in fp32, adds the folded
-//      bias, rounds to bf16 and stores them swizzled in shared memory;
+//      projection) with 16-byte vector loads, blends the 4 taps on top of the folded
+//      bias with packed bf16 FMAs and stores them swizzled in shared memory;
 //   3. runs S = Q K^T (+ relative position bias, key mask), an online softmax over all sources and
-//      O += P V on the tensor cores, fp32 accumulation, one warp per 16 query rows and all 8 heads.
+//      O += P V on the tensor cores, fp32 accumulation, one warp per 16 query rows x 4 heads (8 warps).
 // Sources with no visible key in this group are skipped entirely (their softmax weight is exactly 0).
 // window / grid partition differ only in the token table (hetero_fusion.py:384-389 vs 427-431).
 //
@@ -39,7 +39,7 @@ struct AttnParams {
   __nv_bfloat16* out;          // [B*L*N][256]
 };
 
-constexpr int kAttnThreads = 128;
+constexpr int kAttnThreads = 256;
 constexpr int kTileBytes = kS * kC * 2;          // 32 KB: 64 tokens x 256 ch bf16
 constexpr int kBiasStride = 232;                 // [8 heads][225 (+7 pad)]
 struct TapRec { int x0, y0; float w00, w01, w10, w11; int vis; int pad; };
@@ -62,6 +62,11 @@ HMVIT_DEVINL void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 HMVIT_DEVINL float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+HMVIT_DEVINL uint32_t hfma2_bf16(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 
 // flat token index of slot s in group (gy, gx)
 HMVIT_DEVINL void group_token(int kind, int gy, int gx, int s, int H, int W, int& r, int& c) {
@@ -70,6 +75,8 @@ HMVIT_DEVINL void group_token(int kind, int gy, int gx, int s, int H, int W, int
   else           { r = s1 * (H / kWin) + gy; c = s2 * (W / kWin) + gx; }
 }
 
+// 8 warps: warp = (head group hg = warp / 4, query row block rb = warp % 4); each warp owns 16 query
+// rows x 4 heads.  All 8 warps share the gather of every source's K / V tile.
 __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnParams p) {
   const int a = blockIdx.y;
   const int b = a / p.L, i = a - b * p.L;
@@ -80,35 +87,36 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
   const int gy = blockIdx.x / GX, gx = blockIdx.x - gy * GX;
   const int te = p.mode[a] != 0 ? 1 : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rb = warp & 3, hg = warp >> 2;
   const int g = lane >> 2, t = lane & 3;
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTileBytes;
   uint8_t* sV = smem + 2 * kTileBytes;
-  float* sBias = reinterpret_cast<float*>(smem + 3 * kTileBytes);          // [8][kBiasStride]
+  float* sBias = reinterpret_cast<float*>(smem + 3 * kTileBytes);          // [8][kBiasStride], log2 domain
   TapRec* sTap = reinterpret_cast<TapRec*>(sBias + kHeads * kBiasStride);  // [64]
 
-  // ---- stage Q (ego rows) and the bias table ----
+  // ---- stage Q (ego rows; softmax scale and log2(e) are folded into W_q) and the bias table ----
   {
     const uint4* qsrc = reinterpret_cast<const uint4*>(p.q) + static_cast<size_t>(a) * N * 32;
 #pragma unroll 4
-    for (int tt = 0; tt < 16; ++tt) {
-      const int s = warp * 16 + tt;
+    for (int tt = 0; tt < 8; ++tt) {
+      const int s = warp * 8 + tt;
       int r, c; group_token(p.kind, gy, gx, s, p.H, p.W, r, c);
       const uint4 v = __ldg(qsrc + static_cast<size_t>(r * p.W + c) * 32 + lane);
       *reinterpret_cast<uint4*>(sQ + tile_off(s, lane)) = v;
     }
     for (int e = threadIdx.x; e < 225 * kHeads; e += kAttnThreads) {
       const int idx = e >> 3, h = e & 7;
-      sBias[h * kBiasStride + idx] = __ldg(p.bias_table + e) * 1.4426950408889634f;   // log2(e) folded
+      sBias[h * kBiasStride + idx] = __ldg(p.bias_table + e) * 1.4426950408889634f;
     }
   }
 
-  float o[kHeads][4][4];
-  float mrow[kHeads][2], lrow[kHeads][2];
+  float o[4][4][4];
+  float mrow[4][2], lrow[4][2];
 #pragma unroll
-  for (int h = 0; h < kHeads; ++h) {
+  for (int h = 0; h < 4; ++h) {
     mrow[h][0] = mrow[h][1] = -INFINITY; lrow[h][0] = lrow[h][1] = 0.f;
 #pragma unroll
     for (int n = 0; n < 4; ++n) { o[h][n][0] = o[h][n][1] = o[h][n][2] = o[h][n][3] = 0.f; }
@@ -116,6 +124,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
 
   const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
   const size_t plane = static_cast<size_t>(p.B) * p.L * N * 32;            // uint4 units per te plane
+  // relative-position bias index of (query row g | g+8 of block rb, key nt*8 + 2t + e):
+  //   ((2rb [+1]) - nt + 7) * 15 + (g - (2t + e) + 7)  =  bias_base - 15 nt - e  [+ 15]
+  const int bias_base = (2 * rb + 7) * 15 + (g - 2 * t + 7);
 
   for (int j = 0; j < nrec; ++j) {
     if (p.cav_mask[b * p.L + j] == 0) continue;
@@ -132,28 +143,26 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
       rec.vis = vis; rec.pad = 0;
       sTap[threadIdx.x] = rec;
     }
-    if (!__syncthreads_or(vis)) continue;      // also orders sTap writes / previous compute phase
+    if (!__syncthreads_or(vis)) continue;      // source invisible in this group: its softmax weight is exactly 0
 
-    // ---- gather projected K / V rows of source j (bilinear, + folded bias) ----
+    // ---- gather projected K / V rows of source j: 4-tap blend with packed bf16 FMAs, + folded bias ----
     {
       const int tj = p.mode[b * p.L + j] != 0 ? 1 : 0;
       const uint4* ksrc = reinterpret_cast<const uint4*>(p.k) + te * plane + static_cast<size_t>(b * p.L + j) * N * 32 + lane;
       const uint4* vsrc = reinterpret_cast<const uint4*>(p.v) + te * plane + static_cast<size_t>(b * p.L + j) * N * 32 + lane;
-      float bkr[8], bvr[8];
+      uint32_t bk2[4], bv2[4];
       {
         const float4* pk = reinterpret_cast<const float4*>(p.bk + (te * 2 + tj) * kC + lane * 8);
         const float4* pv = reinterpret_cast<const float4*>(p.bv + (te * 2 + tj) * kC + lane * 8);
         const float4 k0 = __ldg(pk), k1 = __ldg(pk + 1), v0 = __ldg(pv), v1 = __ldg(pv + 1);
-        bkr[0] = k0.x; bkr[1] = k0.y; bkr[2] = k0.z; bkr[3] = k0.w; bkr[4] = k1.x; bkr[5] = k1.y; bkr[6] = k1.z; bkr[7] = k1.w;
-        bvr[0] = v0.x; bvr[1] = v0.y; bvr[2] = v0.z; bvr[3] = v0.w; bvr[4] = v1.x; bvr[5] = v1.y; bvr[6] = v1.z; bvr[7] = v1.w;
+        bk2[0] = pack_bf16x2(k0.x, k0.y); bk2[1] = pack_bf16x2(k0.z, k0.w); bk2[2] = pack_bf16x2(k1.x, k1.y); bk2[3] = pack_bf16x2(k1.z, k1.w);
+        bv2[0] = pack_bf16x2(v0.x, v0.y); bv2[1] = pack_bf16x2(v0.z, v0.w); bv2[2] = pack_bf16x2(v1.x, v1.y); bv2[3] = pack_bf16x2(v1.z, v1.w);
       }
 #pragma unroll 2
-      for (int tt = 0; tt < 16; ++tt) {
-        const int s = warp * 16 + tt;
+      for (int tt = 0; tt < 8; ++tt) {
+        const int s = warp * 8 + tt;
         const TapRec rec = sTap[s];
-        float ka[8], va[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { ka[e] = 0.f; va[e] = 0.f; }
+        uint4 ko = make_uint4(0, 0, 0, 0), vo = make_uint4(0, 0, 0, 0);
         if (rec.vis) {
           const float w4[4] = {rec.w00, rec.w01, rec.w10, rec.w11};
           uint4 kk[4], vv[4];
@@ -166,45 +175,48 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
               kk[q] = __ldg(ksrc + off); vv[q] = __ldg(vsrc + off);
             }
           }
+          ko = make_uint4(bk2[0], bk2[1], bk2[2], bk2[3]);
+          vo = make_uint4(bv2[0], bv2[1], bv2[2], bv2[3]);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float w = w4[q];
-            ka[0] += w * bf16_lo(kk[q].x); ka[1] += w * bf16_hi(kk[q].x); ka[2] += w * bf16_lo(kk[q].y); ka[3] += w * bf16_hi(kk[q].y);
-            ka[4] += w * bf16_lo(kk[q].z); ka[5] += w * bf16_hi(kk[q].z); ka[6] += w * bf16_lo(kk[q].w); ka[7] += w * bf16_hi(kk[q].w);
-            va[0] += w * bf16_lo(vv[q].x); va[1] += w * bf16_hi(vv[q].x); va[2] += w * bf16_lo(vv[q].y); va[3] += w * bf16_hi(vv[q].y);
-            va[4] += w * bf16_lo(vv[q].z); va[5] += w * bf16_hi(vv[q].z); va[6] += w * bf16_lo(vv[q].w); va[7] += w * bf16_hi(vv[q].w);
+            const uint32_t w2 = pack_bf16x2(w4[q], w4[q]);
+            ko.x = hfma2_bf16(w2, kk[q].x, ko.x); ko.y = hfma2_bf16(w2, kk[q].y, ko.y);
+            ko.z = hfma2_bf16(w2, kk[q].z, ko.z); ko.w = hfma2_bf16(w2, kk[q].w, ko.w);
+            vo.x = hfma2_bf16(w2, vv[q].x, vo.x); vo.y = hfma2_bf16(w2, vv[q].y, vo.y);
+            vo.z = hfma2_bf16(w2, vv[q].z, vo.z); vo.w = hfma2_bf16(w2, vv[q].w, vo.w);
           }
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { ka[e] += bkr[e]; va[e] += bvr[e]; }
         }
-        uint4 ko, vo;
-        ko.x = pack_bf16x2(ka[0], ka[1]); ko.y = pack_bf16x2(ka[2], ka[3]); ko.z = pack_bf16x2(ka[4], ka[5]); ko.w = pack_bf16x2(ka[6], ka[7]);
-        vo.x = pack_bf16x2(va[0], va[1]); vo.y = pack_bf16x2(va[2], va[3]); vo.z = pack_bf16x2(va[4], va[5]); vo.w = pack_bf16x2(va[6], va[7]);
         *reinterpret_cast<uint4*>(sK + tile_off(s, lane)) = ko;
         *reinterpret_cast<uint4*>(sV + tile_off(s, lane)) = vo;
       }
     }
     __syncthreads();
 
-    // ---- key visibility bits for this thread's columns: key s' = nt*8 + 2t + e ----
-    uint32_t vbits = 0;            // bit (nt*2 + e)
+    // ---- key visibility bits for this thread's columns: key s' = nt*8 + 2t + e -> bit nt*2 + e ----
+    uint32_t vbits = 0;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       vbits |= (sTap[nt * 8 + 2 * t].vis ? 1u : 0u) << (nt * 2);
       vbits |= (sTap[nt * 8 + 2 * t + 1].vis ? 1u : 0u) << (nt * 2 + 1);
     }
 
-    // ---- tensor-core phase: this warp's 16 query rows x all heads ----
+    // ---- tensor-core phase: this warp's 16 query rows x 4 heads ----
 #pragma unroll
-    for (int h = 0; h < kHeads; ++h) {
+    for (int hh = 0; hh < 4; ++hh) {
+      const int h = hg * 4 + hh;
+      // accumulators start from the relative position bias (log2 domain)
+      const float* bh = sBias + h * kBiasStride + bias_base;
       float sacc[8][4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+      for (int nt = 0; nt < 8; ++nt) {
+        sacc[nt][0] = bh[-15 * nt];      sacc[nt][1] = bh[-15 * nt - 1];
+        sacc[nt][2] = bh[-15 * nt + 15]; sacc[nt][3] = bh[-15 * nt + 14];
+      }
 #pragma unroll
       for (int kk2 = 0; kk2 < 2; ++kk2) {                       // 2 x k16 over the 32 head dims
         uint32_t a0, a1, a2, a3;
         {
-          const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int row = rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
           const int unit = h * 4 + kk2 * 2 + (lane >> 4);
           ldsm_x4(sQ_u + tile_off(row, unit), a0, a1, a2, a3);
         }
@@ -218,29 +230,28 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
           mma_bf16(sacc[np * 2 + 1], a0, a1, a2, a3, b2, b3);
         }
       }
-      // bias + mask (log2 domain), running max
-      const float* bh = sBias + h * kBiasStride;
+      // key mask, running max
       float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (vbits != 0xffffu) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            if (!((vbits >> (nt * 2 + e)) & 1u)) { sacc[nt][e] = -INFINITY; sacc[nt][2 + e] = -INFINITY; }
+          }
+        }
+      }
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int cs = 2 * t + e;                              // key column within its slot row nt
-          // query slot rows: 2*warp (row g) and 2*warp+1 (row g+8); query slot col = g
-          const int i0 = (2 * warp - nt + 7) * 15 + (g - cs + 7);
-          const bool ok = (vbits >> (nt * 2 + e)) & 1u;
-          const float x0 = ok ? fmaf(sacc[nt][e], 1.4426950408889634f, bh[i0]) : -INFINITY;
-          const float x1 = ok ? fmaf(sacc[nt][2 + e], 1.4426950408889634f, bh[i0 + 15]) : -INFINITY;
-          sacc[nt][e] = x0; sacc[nt][2 + e] = x1;
-          mx0 = fmaxf(mx0, x0); mx1 = fmaxf(mx1, x1);
-        }
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(mrow[h][0], mx0), mn1 = fmaxf(mrow[h][1], mx1);
+      const float mn0 = fmaxf(mrow[hh][0], mx0), mn1 = fmaxf(mrow[hh][1], mx1);
       const float mu0 = (mn0 == -INFINITY) ? 0.f : mn0, mu1 = (mn1 == -INFINITY) ? 0.f : mn1;
-      const float al0 = ex2(mrow[h][0] - mu0), al1 = ex2(mrow[h][1] - mu1);
-      mrow[h][0] = mn0; mrow[h][1] = mn1;
+      const float al0 = ex2(mrow[hh][0] - mu0), al1 = ex2(mrow[hh][1] - mu1);
+      mrow[hh][0] = mn0; mrow[hh][1] = mn1;
       float rs0 = 0.f, rs1 = 0.f;
       uint32_t pa[4][4];                                         // P as A fragments: 4 x k16 over the 64 keys
 #pragma unroll
@@ -253,9 +264,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
       }
       rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
       rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
-      lrow[h][0] = lrow[h][0] * al0 + rs0; lrow[h][1] = lrow[h][1] * al1 + rs1;
+      lrow[hh][0] = lrow[hh][0] * al0 + rs0; lrow[hh][1] = lrow[hh][1] * al1 + rs1;
 #pragma unroll
-      for (int n = 0; n < 4; ++n) { o[h][n][0] *= al0; o[h][n][1] *= al0; o[h][n][2] *= al1; o[h][n][3] *= al1; }
+      for (int n = 0; n < 4; ++n) { o[hh][n][0] *= al0; o[hh][n][1] *= al0; o[hh][n][2] *= al1; o[hh][n][3] *= al1; }
       // O_h += P V_h
 #pragma unroll
       for (int kc = 0; kc < 4; ++kc) {
@@ -265,34 +276,35 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
           const int row = kc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
           const int unit = h * 4 + np * 2 + (lane >> 4);
           ldsm_x4_t(sV_u + tile_off(row, unit), b0, b1, b2, b3);
-          mma_bf16(o[h][np * 2], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], b0, b1);
-          mma_bf16(o[h][np * 2 + 1], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], b2, b3);
+          mma_bf16(o[hh][np * 2], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], b0, b1);
+          mma_bf16(o[hh][np * 2 + 1], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], b2, b3);
         }
       }
     }
     __syncthreads();     // compute phase done before sTap / sK / sV are rewritten for the next source
   }
 
-  // ---- normalise, stage in smem (reuse sK after a barrier), coalesced store ----
+  // ---- normalise, stage in smem (reuse sK), coalesced store ----
   __syncthreads();
 #pragma unroll
-  for (int h = 0; h < kHeads; ++h) {
-    const float il0 = lrow[h][0] > 0.f ? 1.0f / lrow[h][0] : 0.f;
-    const float il1 = lrow[h][1] > 0.f ? 1.0f / lrow[h][1] : 0.f;
+  for (int hh = 0; hh < 4; ++hh) {
+    const int h = hg * 4 + hh;
+    const float il0 = lrow[hh][0] > 0.f ? 1.0f / lrow[hh][0] : 0.f;
+    const float il1 = lrow[hh][1] > 0.f ? 1.0f / lrow[hh][1] : 0.f;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
       const int col = h * kDh + n * 8 + 2 * t;                   // channel
-      const int r0 = warp * 16 + g, r1 = r0 + 8;
-      *reinterpret_cast<uint32_t*>(sK + tile_off(r0, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[h][n][0] * il0, o[h][n][1] * il0);
-      *reinterpret_cast<uint32_t*>(sK + tile_off(r1, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[h][n][2] * il1, o[h][n][3] * il1);
+      const int r0 = rb * 16 + g, r1 = r0 + 8;
+      *reinterpret_cast<uint32_t*>(sK + tile_off(r0, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[hh][n][0] * il0, o[hh][n][1] * il0);
+      *reinterpret_cast<uint32_t*>(sK + tile_off(r1, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[hh][n][2] * il1, o[hh][n][3] * il1);
     }
   }
   __syncthreads();
   {
     uint4* dst = reinterpret_cast<uint4*>(p.out) + static_cast<size_t>(a) * N * 32;
 #pragma unroll 4
-    for (int tt = 0; tt < 16; ++tt) {
-      const int s = warp * 16 + tt;
+    for (int tt = 0; tt < 8; ++tt) {
+      const int s = warp * 8 + tt;
       int r, c; group_token(p.kind, gy, gx, s, p.H, p.W, r, c);
       dst[static_cast<size_t>(r * p.W + c) * 32 + lane] = *reinterpret_cast<const uint4*>(sK + tile_off(s, lane));
     }

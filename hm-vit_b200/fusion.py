@@ -26,6 +26,7 @@ from torch import nn
 from . import _lib, ops
 
 _NUM_TYPES = 2
+_LOG2E = 1.4426950408889634
 
 
 # ----------------------------------------------------------------------------------------------
@@ -153,8 +154,9 @@ class HeteroAttention(nn.Module):
         bk = torch.empty(2, 2, Cd, device=att.device)
         bv = torch.empty(2, 2, Cd, device=att.device)
         for t in range(2):
-            wq = self.q_linears[t].weight.detach().float() * self.scale
-            bq = self.q_linears[t].bias.detach().float() * self.scale
+            # softmax scale and log2(e) folded into the query projection (the kernel works in the exp2 domain)
+            wq = self.q_linears[t].weight.detach().float() * (self.scale * _LOG2E)
+            bq = self.q_linears[t].bias.detach().float() * (self.scale * _LOG2E)
             wk = self.k_linears[t].weight.detach().float().view(h, d, Cd)
             bkt = self.k_linears[t].bias.detach().float().view(h, d)
             wv = self.v_linears[t].weight.detach().float().view(h, d, Cd)

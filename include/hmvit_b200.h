@@ -115,7 +115,7 @@ typedef struct {
   const int32_t* cav_mask;
   const float* T;             /* [B][L][L][16] */
   double cell;                /* voxel_size[0] * downsample_rate */
-  const void* q;              /* bf16 rows [B*L*N][256] (softmax scale folded into W_q) */
+  const void* q;              /* bf16 rows [B*L*N][256]; W_q pre-multiplied by dim_head^-0.5 * log2(e) */
   const void* k;              /* bf16 rows [2 (ego type)][B*L*N][256], relation_att folded */
   const void* v;              /* bf16 rows [2 (ego type)][B*L*N][256], relation_msg folded */
   const float* bk;            /* [2 (ego type)][2 (source type)][256] folded key bias */
@@ -142,7 +142,7 @@ int hmvit_roi_cav_mask(const float* T, const int32_t* cav_mask, float* out, int3
  * HeteroFusion.forward            opencood/models/bevformer_point_pillar_hetero.py:39-49
  * HeteroFusionBlock.forward       opencood/models/sub_modules/hetero_fusion.py:446-458 (head == 0) */
 typedef struct {
-  const void* wqkv[2];        /* bf16 [1280][256] per source type: {Wq*scale, A(te=0)Wk, A(te=1)Wk, M(te=0)^T Wv, M(te=1)^T Wv} */
+  const void* wqkv[2];        /* bf16 [1280][256] per source type: {Wq*scale*log2e, A(te=0)Wk, A(te=1)Wk, M(te=0)^T Wv, M(te=1)^T Wv} */
   const float* bqkv;          /* [2][1280] (zero for the K / V columns) */
   const float* bk;            /* [2][2][256] */
   const float* bv;            /* [2][2][256] */

@@ -60,9 +60,10 @@ def test_packed_weights_match_emulation_folding():
     ref = E.pack_attention_weights(P, "hetero_fusion_block.grid_attention")
     for t in (0, 1):
         w = pk[f"wqkv{t}"].float()
-        exp = torch.cat([ref["wq"][t], ref["wk"][0][t], ref["wk"][1][t], ref["wv"][0][t], ref["wv"][1][t]], 0)
-        assert torch.equal(w, exp.to(torch.bfloat16).float())
-        assert torch.allclose(pk["bqkv"][t, :256], ref["bq"][t])
+        exp = torch.cat([ref["wq"][t] * 1.4426950408889634, ref["wk"][0][t], ref["wk"][1][t], ref["wv"][0][t], ref["wv"][1][t]], 0)
+        assert torch.equal(w[256:], exp[256:].to(torch.bfloat16).float())
+        assert torch.allclose(w[:256], exp[:256], rtol=2 ** -8, atol=1e-6)       # bf16 storage of the folded W_q
+        assert torch.allclose(pk["bqkv"][t, :256], ref["bq"][t] * 1.4426950408889634)
         assert float(pk["bqkv"][t, 256:].abs().max()) == 0.0
         for te in (0, 1):
             assert torch.allclose(pk["bk"][te, t], ref["bk"][te][t], atol=1e-7)
