@@ -4,6 +4,7 @@
 #include "rowgemm.cuh"
 #include "attn.cuh"
 #include "chain.cuh"
+#include "qkv.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -55,6 +56,33 @@ static int make_weight_tmap(CUtensorMap* map, const void* w, long long n_out, in
 // ------------------------------------------------------------------------------------------------
 // row-GEMM
 // ------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <bool kLN>
+static int launch_qkv(const CUtensorMap& m0, const CUtensorMap& m1, const QkvParams& p, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(qkv_kernel<kLN>, cudaFuncAttributeMaxDynamicSharedMemorySize, QkvCfg::SMEM_BYTES);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  const long long tiles = static_cast<long long>(p.B) * p.L * ((p.N + QkvCfg::BM - 1) / QkvCfg::BM);
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  qkv_kernel<kLN><<<grid, QkvCfg::THREADS, QkvCfg::SMEM_BYTES, st>>>(m0, m1, p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
 template <int ES, int PRO, int EPI>
 static int launch_rowgemm(const CUtensorMap& m0, const CUtensorMap& m1, const RowGemmParams& p, cudaStream_t st) {
   using Cfg = RowGemmCfg<ES>;
@@ -96,13 +124,13 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (variant) {
     case HMVIT_GEMM_QKV:
-      p.a_cm = static_cast<const float*>(a->a); p.out_rows = static_cast<__nv_bfloat16*>(a->out);
-      p.qkv_select = 1; p.qkv_ego_only = a->ego_only ? 1 : 0;
-      return launch_rowgemm<2, PRO_CM_LN, EPI_ROWS_BF16>(m0, m1, p, st);
-    case HMVIT_GEMM_QKV_NOLN:
-      p.a_cm = static_cast<const float*>(a->a); p.out_rows = static_cast<__nv_bfloat16*>(a->out);
-      p.qkv_select = 1; p.qkv_ego_only = a->ego_only ? 1 : 0;
-      return launch_rowgemm<2, PRO_CM_CAST, EPI_ROWS_BF16>(m0, m1, p, st);
+    case HMVIT_GEMM_QKV_NOLN: {
+      QkvParams q;
+      q.B = a->B; q.L = a->L; q.N = a->N; q.mode = a->mode; q.record_len = a->record_len; q.ego_only = a->ego_only ? 1 : 0;
+      q.x_cm = static_cast<const float*>(a->a); q.ln_gamma = a->ln_gamma; q.ln_beta = a->ln_beta; q.ln_eps = a->ln_eps;
+      q.bias = a->bias; q.out_rows = static_cast<__nv_bfloat16*>(a->out);
+      return variant == HMVIT_GEMM_QKV ? launch_qkv<true>(m0, m1, q, st) : launch_qkv<false>(m0, m1, q, st);
+    }
     case HMVIT_GEMM_OUT:
       p.a_rows = static_cast<const __nv_bfloat16*>(a->a); p.out_cm = static_cast<float*>(a->out);
       p.tile_ego_only = a->ego_only ? 1 : 0;
@@ -131,18 +159,6 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
 // ------------------------------------------------------------------------------------------------
 // fused output projection + FFN chain
 // ------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
-static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_num_sms = n;
-    else
-      g_num_sms = 148;
-  }
-  return g_num_sms;
-}
-
 extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a != nullptr, "chain: null args");
   HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->N > 0, "chain: B, L, N must be positive");

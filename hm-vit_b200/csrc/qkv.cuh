@@ -1,0 +1,276 @@
+// Typed LayerNorm + Q / K' / V' projection (sm_100a, persistent, warp-specialised tcgen05 GEMM).
+//
+//   [Q | K'(te=0) | K'(te=1) | V'(te=0) | V'(te=1)] (bf16 rows) = LN_type(x)[128 x 256] * W_type^T [256 x 1280] + b
+//
+// Replaces HeteroLayerNorm (base_transformer.py:171-177) + HeteroAttention.to_qkv
+// (hetero_fusion.py:111-140) + get_hetero_edge_weights (:154-185; relation_att / relation_msg are
+// folded into W_k / W_v on the host) for every valid agent of every scene in one launch.
+//
+// One CTA per SM loops over 128-token tiles.  Warp roles (10 warps):
+//   warps 6-9  A producers: typed LayerNorm of the NEXT tile (channel-major fp32 -> bf16, UMMA
+//              SWIZZLE_128B layout) into one of two A buffers, overlapped with the current tile's MMAs
+//   warp 4     TMA producer: weight stages (128 output channels x 128 B of K), 3-deep ring
+//   warp 5     MMA issuer: 16 x tcgen05.mma (M128 N128 K16) per 128-column chunk, 2 TMEM buffers
+//   warps 0-3  epilogue: TMEM -> +bias -> bf16 -> swizzled smem staging -> fully coalesced row stores
+// Only the chunks a scene needs are computed (K'/V' for the ego types present; in the last stage Q
+// for slot 0 only).
+#pragma once
+#include "common.cuh"
+#include <cuda.h>
+
+namespace hmvit {
+
+struct QkvParams {
+  int B, L, N;
+  const int* mode;             // [B*L]
+  const int* record_len;       // [B]
+  int ego_only;                // Q only for slot 0, K'/V' only for te = type(slot 0)
+  const float* x_cm;           // [B*L][256][N] fp32
+  const float* ln_gamma;       // [2][256]
+  const float* ln_beta;        // [2][256]
+  float ln_eps;
+  const float* bias;           // [2][1280]
+  __nv_bfloat16* out_rows;     // [5][B*L*N][256]
+};
+
+struct QkvCfg {
+  static constexpr int BM = 128, BN = 128;
+  static constexpr int CHUNK = 16384;
+  static constexpr int NCHA = 4;                       // A chunks (bf16, K = 256)
+  static constexpr int NS = 3;                         // weight ring stages
+  static constexpr int N_CHUNKS = 10;                  // 1280 / 128
+  static constexpr int A_BYTES = NCHA * CHUNK;         // 64 KB per A buffer
+  static constexpr int STAGE_BYTES = 4 * 32 * 256;     // epilogue staging: 4 warps x 32 rows x 256 B
+  static constexpr int SMEM_BYTES = 2 * A_BYTES + NS * CHUNK + STAGE_BYTES + 256 + 1024;
+  static constexpr int THREADS = 320;
+  static constexpr uint32_t TMEM_COLS = 256;
+};
+
+template <bool kLN>
+__global__ void __launch_bounds__(320, 1)
+qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, const QkvParams p) {
+  using Cfg = QkvCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* sA = smem;                                   // [2][A_BYTES]
+  uint8_t* sB = sA + 2 * Cfg::A_BYTES;                  // [NS][CHUNK]
+  uint8_t* sStage = sB + Cfg::NS * Cfg::CHUNK;          // [4][32][256 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGE_BYTES);
+  uint64_t* b_full = bars;                  // [NS]
+  uint64_t* b_empty = b_full + Cfg::NS;     // [NS]
+  uint64_t* acc_full = b_empty + Cfg::NS;   // [2]
+  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint64_t* a_full = acc_empty + 2;         // [2]
+  uint64_t* a_empty = a_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::NS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128);
+      mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_agent = (p.N + Cfg::BM - 1) / Cfg::BM;
+  const int total_tiles = p.B * p.L * tiles_per_agent;
+
+  // tile -> (agent, first token, chunk mask); false for padded agent slots
+  auto tile_info = [&](int t, int& a, int& tok0, uint32_t& chunk_mask) -> bool {
+    a = t / tiles_per_agent;
+    tok0 = (t - a * tiles_per_agent) * Cfg::BM;
+    const int b = a / p.L, l = a - b * p.L;
+    const int nrec = p.record_len[b];
+    if (l >= nrec) return false;
+    uint32_t te_mask = 0;
+    if (p.ego_only) te_mask = 1u << (p.mode[b * p.L] != 0 ? 1 : 0);
+    else for (int j = 0; j < nrec; ++j) te_mask |= 1u << (p.mode[b * p.L + j] != 0 ? 1 : 0);
+    uint32_t m = 0;
+    if (!p.ego_only || l == 0) m |= 0x3u;                     // Q
+    if (te_mask & 1u) m |= (0x3u << 2) | (0x3u << 6);         // K'|te=0, V'|te=0
+    if (te_mask & 2u) m |= (0x3u << 4) | (0x3u << 8);         // K'|te=1, V'|te=1
+    chunk_mask = m;
+    return true;
+  };
+
+  if (warp < 4) {
+    // ============================ epilogue ============================
+    const int row = threadIdx.x;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    uint8_t* stg = sStage + warp * (32 * 256);
+    const size_t rows_total = static_cast<size_t>(p.B) * p.L * p.N;
+    uint32_t ci = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int a, tok0; uint32_t chunk_mask;
+      if (!tile_info(t, a, tok0, chunk_mask)) continue;
+      const int type = p.mode[a] != 0 ? 1 : 0;
+      for (int c = 0; c < Cfg::N_CHUNKS; ++c) {
+        if (!((chunk_mask >> c) & 1u)) continue;
+        const uint32_t buf = ci & 1u;
+        mbar_wait(&acc_full[buf], (ci >> 1) & 1u);
+        tc_fence_after();
+        const float* bias = p.bias + type * (Cfg::N_CHUNKS * Cfg::BN) + c * Cfg::BN;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + q * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k8 = 0; k8 < 4; ++k8) {
+            const float* bb = bias + q * 32 + k8 * 8;
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(r[k8 * 8 + 0]) + __ldg(bb + 0), __uint_as_float(r[k8 * 8 + 1]) + __ldg(bb + 1));
+            pk.y = pack_bf16x2(__uint_as_float(r[k8 * 8 + 2]) + __ldg(bb + 2), __uint_as_float(r[k8 * 8 + 3]) + __ldg(bb + 3));
+            pk.z = pack_bf16x2(__uint_as_float(r[k8 * 8 + 4]) + __ldg(bb + 4), __uint_as_float(r[k8 * 8 + 5]) + __ldg(bb + 5));
+            pk.w = pack_bf16x2(__uint_as_float(r[k8 * 8 + 6]) + __ldg(bb + 6), __uint_as_float(r[k8 * 8 + 7]) + __ldg(bb + 7));
+            const int u = q * 4 + k8;
+            *reinterpret_cast<uint4*>(stg + lane * 256 + ((u ^ (lane & 7)) << 4)) = pk;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);           // TMEM buffer drained: the MMA warp may refill it
+        __syncwarp();
+        // coalesced stores: 2 rows (2 x 256 B) per instruction
+        __nv_bfloat16* obase = p.out_rows + (static_cast<size_t>(c >> 1) * rows_total + static_cast<size_t>(a) * p.N + tok0 + warp * 32) * kC +
+                               (c & 1) * Cfg::BN;
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+          const int rr = it * 2 + (lane >> 4), u = lane & 15;
+          const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 256 + ((u ^ (rr & 7)) << 4));
+          if (tok0 + warp * 32 + rr < p.N) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * kC + u * 8) = v;
+        }
+        __syncwarp();
+        ++ci;
+      }
+    }
+    (void)row;
+  } else if (warp == 4) {
+    // ============================ TMA producer (weights) ============================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap0); tma_prefetch_desc(&tmap1);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int a, tok0; uint32_t chunk_mask;
+        if (!tile_info(t, a, tok0, chunk_mask)) continue;
+        const CUtensorMap* tmap = (p.mode[a] != 0) ? &tmap1 : &tmap0;
+        for (int c = 0; c < Cfg::N_CHUNKS; ++c) {
+          if (!((chunk_mask >> c) & 1u)) continue;
+          for (int kc = 0; kc < Cfg::NCHA; ++kc, ++it) {
+            const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
+            mbar_wait(&b_empty[s], ph ^ 1u);
+            mbar_arrive_expect_tx(&b_full[s], Cfg::CHUNK);
+            tma_load_2d(sB + s * Cfg::CHUNK, tmap, &b_full[s], kc * 64, c * Cfg::BN);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(1u, Cfg::BM, Cfg::BN);
+      const uint32_t a_base0 = smem_u32(sA), b_base = smem_u32(sB);
+      uint32_t it = 0, ci = 0, ti = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int a, tok0; uint32_t chunk_mask;
+        if (!tile_info(t, a, tok0, chunk_mask)) continue;
+        const uint32_t ab = ti & 1u;
+        mbar_wait(&a_full[ab], (ti >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_base = a_base0 + ab * Cfg::A_BYTES;
+        for (int c = 0; c < Cfg::N_CHUNKS; ++c) {
+          if (!((chunk_mask >> c) & 1u)) continue;
+          const uint32_t buf = ci & 1u;
+          mbar_wait(&acc_empty[buf], ((ci >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * Cfg::BN;
+          for (int kc = 0; kc < Cfg::NCHA; ++kc, ++it) {
+            const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
+            mbar_wait(&b_full[s], ph);
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss<2>(d_tmem, umma_desc_sw128(a_base + kc * Cfg::CHUNK + ks * 32),
+                         umma_desc_sw128(b_base + s * Cfg::CHUNK + ks * 32), idesc, (kc | ks) != 0 ? 1u : 0u);
+            umma_commit(&b_empty[s]);
+          }
+          umma_commit(&acc_full[buf]);
+          ++ci;
+        }
+        umma_commit(&a_empty[ab]);               // every MMA that reads this A buffer has retired
+        ++ti;
+      }
+    }
+  } else {
+    // ============================ A producers: typed LayerNorm ============================
+    const int row = threadIdx.x - 192;           // 0..127
+    uint32_t ti = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int a, tok0; uint32_t chunk_mask;
+      if (!tile_info(t, a, tok0, chunk_mask)) continue;
+      const int type = p.mode[a] != 0 ? 1 : 0;
+      const uint32_t ab = ti & 1u;
+      const int tok = tok0 + row;
+      const bool valid = tok < p.N;
+      const float* src = p.x_cm + static_cast<size_t>(a) * kC * p.N + (valid ? tok : 0);
+      float mean = 0.f, rstd = 1.f;
+      if constexpr (kLN) {
+        const float s0 = valid ? __ldg(src) : 0.f;
+        float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < kC; c0 += 32) {
+          float xv[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { const float d = xv[e] - s0; sum += d; sq += d * d; }
+        }
+        const float md = sum * (1.0f / kC);
+        mean = s0 + md;
+        rstd = rsqrtf(fmaxf(sq * (1.0f / kC) - md * md, 0.f) + p.ln_eps);
+      }
+      const float* gam = p.ln_gamma + type * kC;
+      const float* bet = p.ln_beta + type * kC;
+      mbar_wait(&a_empty[ab], ((ti >> 1) & 1u) ^ 1u);
+      uint8_t* dstA = sA + ab * Cfg::A_BYTES;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kC; c0 += 32) {
+        float xv[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+        if constexpr (kLN) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) xv[e] = valid ? ((xv[e] - mean) * rstd * __ldg(gam + c0 + e) + __ldg(bet + c0 + e)) : 0.f;
+        }
+#pragma unroll
+        for (int uu = 0; uu < 4; ++uu) {
+          const float* v = xv + uu * 8;
+          const int u = c0 / 8 + uu;
+          uint4 pk;
+          pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
+          pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(dstA + (u >> 3) * Cfg::CHUNK + sw128_offset(row, u & 7)) = pk;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[ab]);
+      ++ti;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace hmvit
