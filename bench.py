@@ -143,6 +143,7 @@ def kernel_breakdown(pkg, net, inp, iters=3):
     hid = torch.empty(Bq, L, C, N_TOK, device=dev)
     xres = torch.empty_like(x)
     out = torch.empty(Bq, C, N_TOK, device=dev)
+    stats = torch.empty(Bq * L * N_TOK, 2, device=dev)
     cell = float(blk.discrete_ratio) * float(blk.downsample_rate)
     common = dict(B=Bq, L=L, N=N_TOK, mode=mode, record_len=rl)
     acc = {}
@@ -161,16 +162,16 @@ def kernel_breakdown(pkg, net, inp, iters=3):
                 dead = net.skip_dead_queries and it == net.num_iters - 1 and kind == 1
                 xsrc = x if (it == 0 and kind == 0) else xres
                 timed("ln_qkv_gemm", lambda: ops.rowgemm(lib.GEMM_QKV, n_out=1280, a=xsrc, w0=w["wqkv0"], w1=w["wqkv1"],
-                                                         bias=w["bqkv"], out=qkv, ln_gamma=w["ln1_g"], ln_beta=w["ln1_b"],
-                                                         ego_only=dead, **common))
+                                                         bias=w["bqkv"], out=qkv, ego_only=dead,
+                                                         ln_stats=None if (it == 0 and kind == 0) else stats, **common))
                 timed("group_attn", lambda: ops.group_attn(B=Bq, L=L, H=H, W=W, kind=kind, mode=mode, record_len=rl,
                                                            cav_mask=cav, T=T, cell=cell, q=qkv[0], k=qkv[1:3], v=qkv[3:5],
                                                            bk=w["bk"], bv=w["bv"], bias_table=w["bias_table"], out=att,
                                                            ego_only=dead))
                 timed("out_ffn_chain", lambda: ops.out_ffn_chain(o=att, resid=xsrc, out=xres, wa0=w["wa0"], wa1=w["wa1"], ba=w["ba"],
-                                                                 ln_gamma=w["ln2_g"], ln_beta=w["ln2_b"], w1_0=w["w1_0"],
-                                                                 w1_1=w["w1_1"], b1=w["b1"], w2_0=w["w2_0"], w2_1=w["w2_1"],
-                                                                 b2=w["b2"], ego_only=dead, **common))
+                                                                 w1_0=w["w1_0"], w1_1=w["w1_1"], b1=w["b1"], w2_0=w["w2_0"],
+                                                                 w2_1=w["w2_1"], b2=w["b2"], ego_only=dead, stats_out=stats,
+                                                                 **common))
         timed("head_gemm", lambda: ops.rowgemm(lib.GEMM_HEAD1, n_out=256, a=xres, w0=hp["w1_0"], w1=hp["w1_1"], bias=hp["b1"],
                                                out=hid, **common))
         timed("head_gemm", lambda: ops.rowgemm(lib.GEMM_HEAD2, n_out=256, a=hid, w0=hp["w2_0"], w1=hp["w2_1"], bias=hp["b2"],

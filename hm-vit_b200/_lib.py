@@ -23,14 +23,15 @@ class RowGemmArgs(C.Structure):
                 ("mode", C.c_void_p), ("record_len", C.c_void_p), ("ego_only", C.c_int32),
                 ("a", C.c_void_p), ("w", C.c_void_p * 2), ("bias", C.c_void_p),
                 ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p), ("ln_eps", C.c_float),
-                ("resid", C.c_void_p), ("out", C.c_void_p)]
+                ("resid", C.c_void_p), ("out", C.c_void_p), ("ln_stats", C.c_void_p)]
 
 
 class ChainArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("N", C.c_int32), ("mode", C.c_void_p), ("record_len", C.c_void_p),
                 ("ego_only", C.c_int32), ("o", C.c_void_p), ("resid", C.c_void_p), ("out", C.c_void_p),
                 ("wa", C.c_void_p * 2), ("ba", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
-                ("ln_eps", C.c_float), ("w1", C.c_void_p * 2), ("b1", C.c_void_p), ("w2", C.c_void_p * 2), ("b2", C.c_void_p)]
+                ("ln_eps", C.c_float), ("w1", C.c_void_p * 2), ("b1", C.c_void_p), ("w2", C.c_void_p * 2), ("b2", C.c_void_p),
+                ("stats_out", C.c_void_p)]
 
 
 class AttnArgs(C.Structure):

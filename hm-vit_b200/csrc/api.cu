@@ -108,7 +108,7 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
   HMVIT_CHECK_ARG(variant >= HMVIT_GEMM_QKV && variant <= HMVIT_GEMM_QKV_NOLN, "rowgemm: unknown variant");
   if (variant == HMVIT_GEMM_QKV || variant == HMVIT_GEMM_QKV_NOLN) HMVIT_CHECK_ARG(a->n_out == 1280, "rowgemm: QKV expects n_out == 1280");
   else HMVIT_CHECK_ARG(a->n_out == 256, "rowgemm: n_out must be 256 for this variant");
-  if (variant == HMVIT_GEMM_QKV || variant == HMVIT_GEMM_FFN1) HMVIT_CHECK_ARG(a->ln_gamma && a->ln_beta, "rowgemm: LayerNorm parameters missing");
+  HMVIT_CHECK_ARG((a->ln_gamma == nullptr) == (a->ln_beta == nullptr), "rowgemm: ln_gamma and ln_beta must both be set or both be null");
   if (variant == HMVIT_GEMM_OUT || variant == HMVIT_GEMM_FFN2) HMVIT_CHECK_ARG(a->resid != nullptr, "rowgemm: residual missing");
 
   CUtensorMap m0, m1;
@@ -128,7 +128,7 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
       QkvParams q;
       q.B = a->B; q.L = a->L; q.N = a->N; q.mode = a->mode; q.record_len = a->record_len; q.ego_only = a->ego_only ? 1 : 0;
       q.x_cm = static_cast<const float*>(a->a); q.ln_gamma = a->ln_gamma; q.ln_beta = a->ln_beta; q.ln_eps = a->ln_eps;
-      q.bias = a->bias; q.out_rows = static_cast<__nv_bfloat16*>(a->out);
+      q.stats_in = reinterpret_cast<const float2*>(a->ln_stats); q.bias = a->bias; q.out_rows = static_cast<__nv_bfloat16*>(a->out);
       return variant == HMVIT_GEMM_QKV ? launch_qkv<true>(m0, m1, q, st) : launch_qkv<false>(m0, m1, q, st);
     }
     case HMVIT_GEMM_OUT:
@@ -162,8 +162,7 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
 extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a != nullptr, "chain: null args");
   HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->N > 0, "chain: B, L, N must be positive");
-  HMVIT_CHECK_ARG(a->mode && a->record_len && a->o && a->resid && a->out && a->wa[0] && a->wa[1] && a->ba && a->ln_gamma &&
-                  a->ln_beta && a->w1[0] && a->w1[1] && a->b1 && a->w2[0] && a->w2[1] && a->b2, "chain: null pointer");
+  HMVIT_CHECK_ARG(a->mode && a->record_len && a->o && a->resid && a->out && a->wa[0] && a->wa[1] && a->ba && a->w1[0] && a->w1[1] && a->b1 && a->w2[0] && a->w2[1] && a->b2, "chain: null pointer");
   ChainMaps maps;
   int rc = make_weight_tmap(&maps.o, a->o, static_cast<long long>(a->B) * a->L * a->N, 2); if (rc) return rc;
   for (int t = 0; t < 2; ++t) {
@@ -174,7 +173,8 @@ extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
   ChainParams p;
   p.B = a->B; p.L = a->L; p.N = a->N; p.mode = a->mode; p.record_len = a->record_len; p.tile_ego_only = a->ego_only ? 1 : 0;
   p.resid_cm = a->resid; p.out_cm = a->out; p.ba = a->ba; p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_eps = a->ln_eps;
-  p.b1 = a->b1; p.b2 = a->b2;
+  p.b1 = a->b1; p.b2 = a->b2; p.stats_out = reinterpret_cast<float2*>(a->stats_out);
+  HMVIT_CHECK_ARG((a->ln_gamma == nullptr) == (a->ln_beta == nullptr), "chain: ln_gamma and ln_beta must both be set or both be null");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -295,7 +295,8 @@ extern "C" size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, 
   size_t bytes = 0;
   bytes += align_up(rows * 256 * 2 * 5, 1024);   // q, k|te0, k|te1, v|te0, v|te1 (bf16 rows)
   bytes += align_up(rows * 256 * 2, 1024);       // attention output (bf16 rows)
-  bytes += align_up(rows * 256 * 4, 1024);       // FFN hidden (fp32 cm, tf32 values)
+  bytes += align_up(rows * 256 * 4, 1024);       // FFN hidden (fp32 cm, tf32 values; unfused path and head)
+  bytes += align_up(rows * 2 * 4, 1024);         // per-row LayerNorm statistics handed from one stage to the next
   return bytes;
 }
 
@@ -316,6 +317,9 @@ extern "C" int hmvit_fusion_forward(const HmvitFusionArgs* a, void* stream) {
   __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws);
   ws += align_up(rows * 256 * 2, 1024);
   float* hid = reinterpret_cast<float*>(ws);
+  ws += align_up(rows * 256 * 4, 1024);
+  float* stats = reinterpret_cast<float*>(ws);
+  bool have_stats = false;                        // stats describe the rows currently in xres
 
   for (int it = 0; it < a->num_iters; ++it) {
     for (int kind = 0; kind < 2; ++kind) {
@@ -328,8 +332,9 @@ extern "C" int hmvit_fusion_forward(const HmvitFusionArgs* a, void* stream) {
       g.B = a->B; g.L = a->L; g.N = N; g.mode = a->mode; g.record_len = a->record_len; g.ego_only = dead; g.ln_eps = a->ln_eps;
       // typed LayerNorm + Q / K' / V' projections
       g.n_out = 1280; g.a = xsrc; g.w[0] = w.wqkv[0]; g.w[1] = w.wqkv[1]; g.bias = w.bqkv;
-      g.ln_gamma = w.ln1_g; g.ln_beta = w.ln1_b; g.out = qkv;
+      g.ln_gamma = w.ln1_g; g.ln_beta = w.ln1_b; g.out = qkv; g.ln_stats = have_stats ? stats : nullptr;
       int rc = hmvit_rowgemm(HMVIT_GEMM_QKV, &g, stream); if (rc) return rc;
+      g.ln_stats = nullptr;
       // warp + mask + attention
       HmvitAttnArgs t;
       memset(&t, 0, sizeof(t));
@@ -347,6 +352,7 @@ extern "C" int hmvit_fusion_forward(const HmvitFusionArgs* a, void* stream) {
         rc = hmvit_rowgemm(HMVIT_GEMM_FFN1, &g, stream); if (rc) return rc;
         g.a = hid; g.w[0] = w.w2[0]; g.w[1] = w.w2[1]; g.bias = w.b2; g.resid = a->xres; g.out = a->xres;
         rc = hmvit_rowgemm(HMVIT_GEMM_FFN2, &g, stream); if (rc) return rc;
+        have_stats = false;
       } else {
         // output projection + residual + pre-norm feed-forward + residual, one kernel
         HmvitChainArgs c;
@@ -355,7 +361,9 @@ extern "C" int hmvit_fusion_forward(const HmvitFusionArgs* a, void* stream) {
         c.o = att; c.resid = xsrc; c.out = a->xres;
         c.wa[0] = w.wa[0]; c.wa[1] = w.wa[1]; c.ba = w.ba; c.ln_gamma = w.ln2_g; c.ln_beta = w.ln2_b; c.ln_eps = a->ln_eps;
         c.w1[0] = w.w1[0]; c.w1[1] = w.w1[1]; c.b1 = w.b1; c.w2[0] = w.w2[0]; c.w2[1] = w.w2[1]; c.b2 = w.b2;
+        c.stats_out = stats;
         rc = hmvit_out_ffn_chain(&c, stream); if (rc) return rc;
+        have_stats = true;
       }
     }
   }

@@ -29,11 +29,12 @@ struct ChainParams {
   const float* resid_cm;       // x   [B*L][256][N]
   float* out_cm;               // x'' [B*L][256][N] (may alias resid_cm)
   const float* ba;             // [2][256]
-  const float* ln_gamma;       // [2][256]
-  const float* ln_beta;        // [2][256]
+  const float* ln_gamma;       // [2][256] or null (affine folded into W_1 / b_1 on the host)
+  const float* ln_beta;        // [2][256] or null
   float ln_eps;
   const float* b1;             // [2][256]
   const float* b2;             // [2][256]
+  float2* stats_out;           // optional [B*L][N] (mean, rstd) of every x'' row: LayerNorm statistics for the next stage
 };
 
 struct ChainMaps {             // TMA tensor maps
@@ -112,54 +113,65 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
       const size_t cm_off = static_cast<size_t>(a) * kC * p.N + (valid ? tok : 0);
       const float* res = p.resid_cm + cm_off;
       float* dst = p.out_cm + cm_off;
-      // ---- E1: x' = D1 + b_a + x ; statistics ----
+      // ---- E1: x' = D1 + b_a + x ; statistics.  The residual loads run 3 pieces ahead and start
+      //      before the projection MMAs have finished. ----
+      float rv[3][32];
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) rv[q][k] = valid ? res[static_cast<size_t>(q * 32 + k) * p.N] : 0.f;
+      }
       mbar_wait(d1_full, ti & 1);
       tc_fence_after();
       float s0 = 0.f, sum = 0.f, sq = 0.f;
-#pragma unroll 1
-      for (int q = 0; q < 8; ++q) {
-        float rv[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) rv[k] = valid ? res[static_cast<size_t>(q * 32 + k) * p.N] : 0.f;
+      for (int q = 0; q < 8; ++q) {
         uint32_t r[32];
         tmem_ld32(D1 + lane_base + q * 32, r);
         tmem_ld_wait();
         const float* bias = p.ba + type * kC + q * 32;
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-          const float v = __uint_as_float(r[k]) + __ldg(bias + k) + rv[k];
+          const float v = __uint_as_float(r[k]) + __ldg(bias + k) + rv[q % 3][k];
           if (q == 0 && k == 0) s0 = v;
           const float d = v - s0;
           sum += d; sq += d * d;
           r[k] = __float_as_uint(v);
         }
         tmem_st32(D1 + lane_base + q * 32, r);
+        if (q + 3 < 8) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) rv[q % 3][k] = valid ? res[static_cast<size_t>((q + 3) * 32 + k) * p.N] : 0.f;
+        }
       }
       tmem_st_wait();
       const float md = sum * (1.0f / kC);
       const float mean = s0 + md;
       const float rstd = rsqrtf(fmaxf(sq * (1.0f / kC) - md * md, 0.f) + p.ln_eps);
       // ---- P2 feed: LN'(x') -> tf32 K-chunks ----
-      const float* gam = p.ln_gamma + type * kC;
-      const float* bet = p.ln_beta + type * kC;
+      const bool affine = p.ln_gamma != nullptr;
+      const float* gam = affine ? p.ln_gamma + type * kC : nullptr;
+      const float* bet = affine ? p.ln_beta + type * kC : nullptr;
+      const float nmr = -mean * rstd;
 #pragma unroll 1
       for (int kc = 0; kc < 8; ++kc, ++itf) {
         const uint32_t fs = itf % Cfg::NF, ph = (itf / Cfg::NF) & 1u;
         uint32_t r[32];
         tmem_ld32(D1 + lane_base + kc * 32, r);
         tmem_ld_wait();
+        if (affine) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            r[k] = __float_as_uint(tf32_rn(fmaf(__uint_as_float(r[k]), rstd, nmr) * __ldg(gam + kc * 32 + k) + __ldg(bet + kc * 32 + k)));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(tf32_rn(fmaf(__uint_as_float(r[k]), rstd, nmr)));
+        }
         mbar_wait(&f_empty[fs], ph ^ 1u);
         uint8_t* dstF = sF + fs * Cfg::CHUNK;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          uint4 pk;
-          const int c = kc * 32 + u * 4;
-          pk.x = __float_as_uint(tf32_rn((__uint_as_float(r[u * 4 + 0]) - mean) * rstd * __ldg(gam + c + 0) + __ldg(bet + c + 0)));
-          pk.y = __float_as_uint(tf32_rn((__uint_as_float(r[u * 4 + 1]) - mean) * rstd * __ldg(gam + c + 1) + __ldg(bet + c + 1)));
-          pk.z = __float_as_uint(tf32_rn((__uint_as_float(r[u * 4 + 2]) - mean) * rstd * __ldg(gam + c + 2) + __ldg(bet + c + 2)));
-          pk.w = __float_as_uint(tf32_rn((__uint_as_float(r[u * 4 + 3]) - mean) * rstd * __ldg(gam + c + 3) + __ldg(bet + c + 3)));
-          *reinterpret_cast<uint4*>(dstF + sw128_offset(row, u)) = pk;
-        }
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<uint4*>(dstF + sw128_offset(row, u)) = make_uint4(r[u * 4], r[u * 4 + 1], r[u * 4 + 2], r[u * 4 + 3]);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&f_full[fs]);
@@ -175,7 +187,7 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
         tmem_ld32(D2 + lane_base + kc * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(tf32_rn(gelu_erf(__uint_as_float(r[k]) + __ldg(b1 + kc * 32 + k))));
+        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(tf32_rn(gelu_erf_fast(__uint_as_float(r[k]) + __ldg(b1 + kc * 32 + k))));
         mbar_wait(&f_empty[fs], ph ^ 1u);
         uint8_t* dstF = sF + fs * Cfg::CHUNK;
 #pragma unroll
@@ -185,19 +197,29 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
         tc_fence_before();
         mbar_arrive(&f_full[fs]);
       }
-      // ---- E2: x'' = D1 + b_2 ----
+      // ---- E2: x'' = D1 + b_2 (+ LayerNorm statistics of x'' for the next stage) ----
       mbar_wait(d1_final, ti & 1);
       tc_fence_after();
       const float* b2 = p.b2 + type * kC;
+      float t0 = 0.f, tsum = 0.f, tsq = 0.f;
 #pragma unroll 1
       for (int q = 0; q < 8; ++q) {
         uint32_t r[32];
         tmem_ld32(D1 + lane_base + q * 32, r);
         tmem_ld_wait();
-        if (valid) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) dst[static_cast<size_t>(q * 32 + k) * p.N] = __uint_as_float(r[k]) + __ldg(b2 + q * 32 + k);
+        for (int k = 0; k < 32; ++k) {
+          const float v = __uint_as_float(r[k]) + __ldg(b2 + q * 32 + k);
+          if (q == 0 && k == 0) t0 = v;
+          const float d = v - t0;
+          tsum += d; tsq += d * d;
+          if (valid) dst[static_cast<size_t>(q * 32 + k) * p.N] = v;
         }
+      }
+      if (p.stats_out != nullptr && valid) {
+        const float tmd = tsum * (1.0f / kC);
+        p.stats_out[static_cast<size_t>(a) * p.N + tok] =
+            make_float2(t0 + tmd, rsqrtf(fmaxf(tsq * (1.0f / kC) - tmd * tmd, 0.f) + p.ln_eps));
       }
       tc_fence_before();
       mbar_arrive(d1_free);

@@ -39,6 +39,24 @@ HMVIT_DEVINL float tf32_rn(float x) {
 
 HMVIT_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// GELU (erf form) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the tf32
+// rounding applied to the result): 2 MUFU + ~12 FMA-class instructions instead of the erff() call.
+HMVIT_DEVINL float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);          // erf(|x| / sqrt 2)
+  const float h = 0.5f * x;
+  return fmaf(copysignf(erf_abs, x), h, h);            // 0.5 x (1 + erf(x / sqrt 2))
+}
+
 // ------------------------------------------------------------------------------------------
 // 128-byte swizzle (UMMA canonical K-major SWIZZLE_128B layout == what TMA SWIZZLE_128B writes)
 // A [rows x 128 B] chunk: row r at r*128, its eight 16-byte units XORed with (r & 7).

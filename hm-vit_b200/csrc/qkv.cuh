@@ -26,9 +26,10 @@ struct QkvParams {
   const int* record_len;       // [B]
   int ego_only;                // Q only for slot 0, K'/V' only for te = type(slot 0)
   const float* x_cm;           // [B*L][256][N] fp32
-  const float* ln_gamma;       // [2][256]
-  const float* ln_beta;        // [2][256]
+  const float* ln_gamma;       // [2][256] or null (affine folded into W / bias on the host)
+  const float* ln_beta;        // [2][256] or null
   float ln_eps;
+  const float2* stats_in;      // optional [B*L][N] (mean, rstd) per row written by the previous stage, or null
   const float* bias;           // [2][1280]
   __nv_bfloat16* out_rows;     // [5][B*L*N][256]
 };
@@ -221,35 +222,51 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
       const float* src = p.x_cm + static_cast<size_t>(a) * kC * p.N + (valid ? tok : 0);
       float mean = 0.f, rstd = 1.f;
       if constexpr (kLN) {
-        const float s0 = valid ? __ldg(src) : 0.f;
-        float sum = 0.f, sq = 0.f;
+        if (p.stats_in != nullptr) {
+          if (valid) { const float2 st = __ldg(p.stats_in + static_cast<size_t>(a) * p.N + tok); mean = st.x; rstd = st.y; }
+        } else {
+          const float s0 = valid ? __ldg(src) : 0.f;
+          float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < kC; c0 += 32) {
-          float xv[32];
+          for (int c0 = 0; c0 < kC; c0 += 64) {
+            float xv[64];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+            for (int e = 0; e < 64; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) { const float d = xv[e] - s0; sum += d; sq += d * d; }
+            for (int e = 0; e < 64; ++e) { const float d = xv[e] - s0; sum += d; sq += d * d; }
+          }
+          const float md = sum * (1.0f / kC);
+          mean = s0 + md;
+          rstd = rsqrtf(fmaxf(sq * (1.0f / kC) - md * md, 0.f) + p.ln_eps);
         }
-        const float md = sum * (1.0f / kC);
-        mean = s0 + md;
-        rstd = rsqrtf(fmaxf(sq * (1.0f / kC) - md * md, 0.f) + p.ln_eps);
       }
-      const float* gam = p.ln_gamma + type * kC;
-      const float* bet = p.ln_beta + type * kC;
-      mbar_wait(&a_empty[ab], ((ti >> 1) & 1u) ^ 1u);
+      const bool affine = kLN && p.ln_gamma != nullptr;
+      const float* gam = affine ? p.ln_gamma + type * kC : nullptr;
+      const float* bet = affine ? p.ln_beta + type * kC : nullptr;
+      const float nmr = -mean * rstd;
       uint8_t* dstA = sA + ab * Cfg::A_BYTES;
+      bool waited = false;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kC; c0 += 32) {
-        float xv[32];
+      for (int c0 = 0; c0 < kC; c0 += 64) {
+        float xv[64];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+        for (int e = 0; e < 64; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
         if constexpr (kLN) {
+          if (affine) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) xv[e] = valid ? ((xv[e] - mean) * rstd * __ldg(gam + c0 + e) + __ldg(bet + c0 + e)) : 0.f;
+            for (int e = 0; e < 64; ++e) xv[e] = fmaf(xv[e], rstd, nmr) * __ldg(gam + c0 + e) + __ldg(bet + c0 + e);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) xv[e] = fmaf(xv[e], rstd, nmr);
+          }
+          if (!valid) {
+#pragma unroll
+            for (int e = 0; e < 64; ++e) xv[e] = 0.f;
+          }
         }
+        if (!waited) { mbar_wait(&a_empty[ab], ((ti >> 1) & 1u) ^ 1u); waited = true; }   // loads above overlap the wait
 #pragma unroll
-        for (int uu = 0; uu < 4; ++uu) {
+        for (int uu = 0; uu < 8; ++uu) {
           const float* v = xv + uu * 8;
           const int u = c0 / 8 + uu;
           uint4 pk;

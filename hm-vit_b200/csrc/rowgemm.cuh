@@ -156,8 +156,9 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         const float var = fmaxf(sq * (1.0f / kC) - md * md, 0.f);
         rstd = rsqrtf(var + p.ln_eps);
       }
-      const float* gam = p.ln_gamma + type * kC;
-      const float* bet = p.ln_beta + type * kC;
+      const bool affine = p.ln_gamma != nullptr;
+      const float* gam = affine ? p.ln_gamma + type * kC : nullptr;
+      const float* bet = affine ? p.ln_beta + type * kC : nullptr;
       constexpr int EPU = 16 / ES;                      // elements per 16-byte unit
       constexpr int UPB = 32 / EPU;                     // units per batch of 32 channels
 #pragma unroll 1
@@ -167,7 +168,10 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         for (int e = 0; e < 32; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
         if constexpr (PRO == PRO_CM_LN) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) xv[e] = valid ? ((xv[e] - mean) * rstd * __ldg(gam + c0 + e) + __ldg(bet + c0 + e)) : 0.f;
+          for (int e = 0; e < 32; ++e) {
+            const float z = (xv[e] - mean) * rstd;
+            xv[e] = valid ? (affine ? z * __ldg(gam + c0 + e) + __ldg(bet + c0 + e) : z) : 0.f;
+          }
         }
 #pragma unroll
         for (int uu = 0; uu < UPB; ++uu) {

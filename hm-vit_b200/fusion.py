@@ -147,7 +147,9 @@ class HeteroAttention(nn.Module):
         _check_supported(dim, dim_head, window_size)
 
     # folded projection weights, see DESIGN.md "exact restructurings"
-    def packed(self) -> Dict[str, torch.Tensor]:
+    def packed(self, ln_gamma=None, ln_beta=None) -> Dict[str, torch.Tensor]:
+        """Folded projection weights.  With ln_gamma / ln_beta ([2][C], per type) the affine of the
+        preceding typed LayerNorm is folded in as well:  W (g*z + b) + c = (W diag g) z + (W b + c)."""
         Cd, h, d = self._dim, self.heads, self._dim_head
         att, msg = self.relation_att.detach().float(), self.relation_msg.detach().float()
         wqkv, bqkv = [], []
@@ -170,8 +172,13 @@ class HeteroAttention(nn.Module):
                 e = te * 2 + t
                 parts.append(torch.einsum("hpq,hpc->hqc", msg[e], wv).reshape(Cd, Cd))
                 bv[te, t] = torch.einsum("hpq,hp->hq", msg[e], bvt).reshape(Cd)
-            wqkv.append(torch.cat(parts, 0).to(torch.bfloat16).contiguous())
-            bqkv.append(torch.cat([bq, bq.new_zeros(4 * Cd)]))
+            wcat = torch.cat(parts, 0)                                   # [5C, C] fp32
+            bcat = torch.cat([bq, bq.new_zeros(4 * Cd)])
+            if ln_gamma is not None:
+                bcat = bcat + wcat @ ln_beta[t].float()
+                wcat = wcat * ln_gamma[t].float()[None, :]
+            wqkv.append(wcat.to(torch.bfloat16).contiguous())
+            bqkv.append(bcat)
         return {
             "wqkv0": wqkv[0], "wqkv1": wqkv[1], "bqkv": torch.stack(bqkv).contiguous(),
             "bk": bk.contiguous(), "bv": bv.contiguous(),
@@ -262,15 +269,20 @@ class HeteroFusionBlock(nn.Module):
         att = getattr(self, f"{kind}_attention")
         norm = getattr(self, f"{kind}_norm")
         ffd = getattr(self, f"{kind}_ffd")
-        pk = att.packed()
-        pk["ln1_g"] = _stack2(lambda t: norm.net[t].weight.detach().float())
-        pk["ln1_b"] = _stack2(lambda t: norm.net[t].bias.detach().float())
-        pk["ln2_g"] = _stack2(lambda t: ffd.norm.net[t].weight.detach().float())
-        pk["ln2_b"] = _stack2(lambda t: ffd.norm.net[t].bias.detach().float())
+        # both typed LayerNorm affines are folded into the GEMM that consumes them (exact algebra), so the
+        # kernels only normalise: z = (x - mean) * rstd
+        g1 = _stack2(lambda t: norm.net[t].weight.detach().float())
+        b1n = _stack2(lambda t: norm.net[t].bias.detach().float())
+        g2 = _stack2(lambda t: ffd.norm.net[t].weight.detach().float())
+        b2n = _stack2(lambda t: ffd.norm.net[t].bias.detach().float())
+        pk = att.packed(g1, b1n)
+        b1 = []
         for t in range(2):
-            pk[f"w1_{t}"] = _tf32_round(ffd.fn.net[t][0].weight)
+            w1 = ffd.fn.net[t][0].weight.detach().float()
+            pk[f"w1_{t}"] = _tf32_round(w1 * g2[t][None, :])
+            b1.append(ffd.fn.net[t][0].bias.detach().float() + w1 @ b2n[t])
             pk[f"w2_{t}"] = _tf32_round(ffd.fn.net[t][3].weight)
-        pk["b1"] = _stack2(lambda t: ffd.fn.net[t][0].bias.detach().float())
+        pk["b1"] = torch.stack(b1).contiguous()
         pk["b2"] = _stack2(lambda t: ffd.fn.net[t][3].bias.detach().float())
         return pk
 
@@ -346,8 +358,7 @@ def _fill_stage(sw: "_lib.StageWeights", pk: Dict[str, torch.Tensor]):
     sw.bqkv, sw.bk, sw.bv = pk["bqkv"].data_ptr(), pk["bk"].data_ptr(), pk["bv"].data_ptr()
     sw.wa[0], sw.wa[1] = pk["wa0"].data_ptr(), pk["wa1"].data_ptr()
     sw.ba = pk["ba"].data_ptr()
-    sw.ln1_g, sw.ln1_b = pk["ln1_g"].data_ptr(), pk["ln1_b"].data_ptr()
-    sw.ln2_g, sw.ln2_b = pk["ln2_g"].data_ptr(), pk["ln2_b"].data_ptr()
+    sw.ln1_g = sw.ln1_b = sw.ln2_g = sw.ln2_b = None      # LayerNorm affines are folded into the weights
     sw.w1[0], sw.w1[1] = pk["w1_0"].data_ptr(), pk["w1_1"].data_ptr()
     sw.w2[0], sw.w2[1] = pk["w2_0"].data_ptr(), pk["w2_1"].data_ptr()
     sw.b1, sw.b2 = pk["b1"].data_ptr(), pk["b2"].data_ptr()

@@ -31,7 +31,7 @@ def _chk(t, dtype, name):
 
 
 def rowgemm(variant, *, B, L, N, n_out, mode, record_len, a, w0, w1, bias, out, ego_only=False,
-            ln_gamma=None, ln_beta=None, ln_eps=1e-5, resid=None):
+            ln_gamma=None, ln_beta=None, ln_eps=1e-5, resid=None, ln_stats=None):
     args = _lib.RowGemmArgs()
     args.B, args.L, args.N, args.n_out = B, L, N, n_out
     args.mode = mode.data_ptr()
@@ -45,19 +45,23 @@ def rowgemm(variant, *, B, L, N, n_out, mode, record_len, a, w0, w1, bias, out, 
     args.ln_eps = ln_eps
     args.resid = resid.data_ptr() if resid is not None else None
     args.out = out.data_ptr()
+    args.ln_stats = ln_stats.data_ptr() if ln_stats is not None else None
     _lib.check(_lib.load().hmvit_rowgemm(variant, C.byref(args), _stream()))
     return out
 
 
-def out_ffn_chain(*, B, L, N, mode, record_len, o, resid, out, wa0, wa1, ba, ln_gamma, ln_beta, w1_0, w1_1, b1, w2_0, w2_1, b2,
-                  ego_only=False, ln_eps=1e-5):
+def out_ffn_chain(*, B, L, N, mode, record_len, o, resid, out, wa0, wa1, ba, w1_0, w1_1, b1, w2_0, w2_1, b2,
+                  ln_gamma=None, ln_beta=None, ego_only=False, ln_eps=1e-5, stats_out=None):
     args = _lib.ChainArgs()
     args.B, args.L, args.N = B, L, N
     args.mode, args.record_len = mode.data_ptr(), record_len.data_ptr()
     args.ego_only = 1 if ego_only else 0
     args.o, args.resid, args.out = o.data_ptr(), resid.data_ptr(), out.data_ptr()
     args.wa[0], args.wa[1] = wa0.data_ptr(), wa1.data_ptr()
-    args.ba, args.ln_gamma, args.ln_beta, args.ln_eps = ba.data_ptr(), ln_gamma.data_ptr(), ln_beta.data_ptr(), ln_eps
+    args.ba, args.ln_eps = ba.data_ptr(), ln_eps
+    args.ln_gamma = ln_gamma.data_ptr() if ln_gamma is not None else None
+    args.ln_beta = ln_beta.data_ptr() if ln_beta is not None else None
+    args.stats_out = stats_out.data_ptr() if stats_out is not None else None
     args.w1[0], args.w1[1], args.b1 = w1_0.data_ptr(), w1_1.data_ptr(), b1.data_ptr()
     args.w2[0], args.w2[1], args.b2 = w2_0.data_ptr(), w2_1.data_ptr(), b2.data_ptr()
     _lib.check(_lib.load().hmvit_out_ffn_chain(C.byref(args), _stream()))

@@ -66,11 +66,13 @@ typedef struct {
   const void* w[2];           /* weights per modality type, row-major [n_out][256]: bf16 for QKV/OUT,
                                  fp32 holding tf32-rounded values for the FFN and HEAD variants */
   const float* bias;          /* [2][n_out] */
-  const float* ln_gamma;      /* [2][256] (QKV, FFN1) */
-  const float* ln_beta;       /* [2][256] */
+  const float* ln_gamma;      /* [2][256] (QKV, FFN1), or NULL when the affine is folded into w / bias */
+  const float* ln_beta;       /* [2][256] or NULL */
   float ln_eps;
   const float* resid;         /* fp32 cm (OUT, FFN2) */
   void* out;                  /* see variant */
+  const float* ln_stats;      /* QKV only, optional: [B*L][N][2] (mean, rstd) of every row of `a`, as written by
+                                 hmvit_out_ffn_chain(stats_out); NULL = compute the statistics in the kernel */
 } HmvitRowGemmArgs;
 
 int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* args, void* stream);
@@ -90,13 +92,15 @@ typedef struct {
   float* out;                 /* x'', fp32 cm [B*L][256][N]; may be the same buffer as resid */
   const void* wa[2];          /* bf16 [256][256] per type */
   const float* ba;            /* [2][256] */
-  const float* ln_gamma;      /* [2][256] */
-  const float* ln_beta;       /* [2][256] */
+  const float* ln_gamma;      /* [2][256], or NULL when the affine is folded into w1 / b1 */
+  const float* ln_beta;       /* [2][256] or NULL */
   float ln_eps;
   const void* w1[2];          /* fp32 (tf32) [256][256] */
   const float* b1;            /* [2][256] */
   const void* w2[2];          /* fp32 (tf32) [256][256] */
   const float* b2;            /* [2][256] */
+  float* stats_out;           /* optional [B*L][N][2]: (mean, rstd) of every output row, the LayerNorm statistics
+                                 the next stage's QKV projection needs; NULL = not written */
 } HmvitChainArgs;
 
 int hmvit_out_ffn_chain(const HmvitChainArgs* args, void* stream);
@@ -143,13 +147,13 @@ int hmvit_roi_cav_mask(const float* T, const int32_t* cav_mask, float* out, int3
  * HeteroFusionBlock.forward       opencood/models/sub_modules/hetero_fusion.py:446-458 (head == 0) */
 typedef struct {
   const void* wqkv[2];        /* bf16 [1280][256] per source type: {Wq*scale*log2e, A(te=0)Wk, A(te=1)Wk, M(te=0)^T Wv, M(te=1)^T Wv} */
-  const float* bqkv;          /* [2][1280] (zero for the K / V columns) */
+  const float* bqkv;          /* [2][1280] (K / V columns: zero, or W beta when the LayerNorm affine is folded) */
   const float* bk;            /* [2][2][256] */
   const float* bv;            /* [2][2][256] */
   const void* wa[2];          /* bf16 [256][256] */
   const float* ba;            /* [2][256] */
-  const float* ln1_g; const float* ln1_b;   /* attention pre-norm  [2][256] */
-  const float* ln2_g; const float* ln2_b;   /* feed-forward pre-norm [2][256] */
+  const float* ln1_g; const float* ln1_b;   /* attention pre-norm  [2][256]; NULL when folded into wqkv / bqkv */
+  const float* ln2_g; const float* ln2_b;   /* feed-forward pre-norm [2][256]; NULL when folded into w1 / b1 */
   const void* w1[2];          /* fp32 (tf32) [256][256] */
   const float* b1;            /* [2][256] */
   const void* w2[2];          /* fp32 (tf32) [256][256] */

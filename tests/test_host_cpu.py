@@ -59,19 +59,21 @@ def test_packed_weights_match_emulation_folding():
     pk = net.hetero_fusion_block.packed()["grid"]
     ref = E.pack_attention_weights(P, "hetero_fusion_block.grid_attention")
     for t in (0, 1):
+        g1 = P[f"hetero_fusion_block.grid_norm.net.{t}.weight"]
+        b1 = P[f"hetero_fusion_block.grid_norm.net.{t}.bias"]
         w = pk[f"wqkv{t}"].float()
         exp = torch.cat([ref["wq"][t] * 1.4426950408889634, ref["wk"][0][t], ref["wk"][1][t], ref["wv"][0][t], ref["wv"][1][t]], 0)
-        assert torch.equal(w[256:], exp[256:].to(torch.bfloat16).float())
-        assert torch.allclose(w[:256], exp[:256], rtol=2 ** -8, atol=1e-6)       # bf16 storage of the folded W_q
-        assert torch.allclose(pk["bqkv"][t, :256], ref["bq"][t] * 1.4426950408889634)
-        assert float(pk["bqkv"][t, 256:].abs().max()) == 0.0
+        expb = torch.cat([ref["bq"][t] * 1.4426950408889634, torch.zeros(1024)]) + exp @ b1     # LayerNorm beta folded
+        assert torch.allclose(w, exp * g1[None, :], rtol=2 ** -8, atol=1e-6)                     # bf16 storage, gamma folded
+        assert torch.allclose(pk["bqkv"][t], expb, atol=1e-5)
         for te in (0, 1):
             assert torch.allclose(pk["bk"][te, t], ref["bk"][te][t], atol=1e-7)
             assert torch.allclose(pk["bv"][te, t], ref["bv"][te][t], atol=1e-7)
     # tf32 rounding keeps 10 mantissa bits
     w1 = pk["w1_0"]
     assert int((w1.view(torch.int32) & 0x1FFF).abs().max()) == 0
-    assert float((w1 - P["hetero_fusion_block.grid_ffd.fn.net.0.0.weight"]).abs().max()) < 1e-3
+    g2 = P["hetero_fusion_block.grid_ffd.norm.net.0.weight"]
+    assert float((w1 - P["hetero_fusion_block.grid_ffd.fn.net.0.0.weight"] * g2[None, :]).abs().max()) < 1e-3
 
 
 def test_regroup_matches_oracle():
