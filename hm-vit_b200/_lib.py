@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhmvit_b200.so")
+LIB_PATH = os.environ.get("HMVIT_LIB", os.path.join(_HERE, "libhmvit_b200.so"))   # HMVIT_LIB: tuning builds only
 
 GEMM_QKV, GEMM_OUT, GEMM_FFN1, GEMM_FFN2, GEMM_HEAD1, GEMM_HEAD2, GEMM_QKV_NOLN = range(7)
 

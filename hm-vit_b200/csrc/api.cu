@@ -39,12 +39,12 @@ static void load_encode() {
       qres == cudaDriverEntryPointSuccess)
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
 }
-static int make_weight_tmap(CUtensorMap* map, const void* w, long long n_out, int es) {
+static int make_weight_tmap(CUtensorMap* map, const void* w, long long n_out, int es, int box_rows = 128) {
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) return fail(HMVIT_ERR_CUDA, "hmvit: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(n_out)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(256) * es};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), 128};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -166,9 +166,9 @@ extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
   ChainMaps maps;
   int rc = make_weight_tmap(&maps.o, a->o, static_cast<long long>(a->B) * a->L * a->N, 2); if (rc) return rc;
   for (int t = 0; t < 2; ++t) {
-    rc = make_weight_tmap(&maps.wa[t], a->wa[t], 256, 2); if (rc) return rc;
-    rc = make_weight_tmap(&maps.w1[t], a->w1[t], 256, 4); if (rc) return rc;
-    rc = make_weight_tmap(&maps.w2[t], a->w2[t], 256, 4); if (rc) return rc;
+    rc = make_weight_tmap(&maps.wa[t], a->wa[t], 256, 2, 256); if (rc) return rc;
+    rc = make_weight_tmap(&maps.w1[t], a->w1[t], 256, 4, 256); if (rc) return rc;
+    rc = make_weight_tmap(&maps.w2[t], a->w2[t], 256, 4, 256); if (rc) return rc;
   }
   ChainParams p;
   p.B = a->B; p.L = a->L; p.N = a->N; p.mode = a->mode; p.record_len = a->record_len; p.tile_ego_only = a->ego_only ? 1 : 0;
@@ -401,3 +401,10 @@ extern "C" int hmvit_debug_probe(uint32_t* out2, void* stream) {
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }
+
+#ifdef HMVIT_TS
+extern "C" int hmvit_debug_chain_ts(unsigned long long* host_out /* [2][16][16] */) {
+  HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_chain_ts, sizeof(unsigned long long) * 2 * 16 * 16));
+  return HMVIT_OK;
+}
+#endif

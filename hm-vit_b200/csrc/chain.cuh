@@ -12,14 +12,28 @@
 //   E1  D1 + b_a + x (channel-major fp32)              -> x' written back to D1, LN statistics
 //   P2  LN'(x') as tf32 32-channel K-chunks (smem ring) x W_1 -> D2                tcgen05 kind::tf32
 //   P3  gelu(D2 + b_1) as tf32 K-chunks (same ring) x W_2     -> accumulated ONTO x' in D1
-//   E2  D1 + b_2                                       -> x'' stored channel-major
-// Warp roles: warps 0-3 transform/epilogue (thread == token row == TMEM lane), warp 4 TMA producer,
-// warp 5 MMA issuer (+ TMEM allocator).
+//   E2  D1 + b_2                                       -> x'' stored channel-major (+ LN statistics)
+// Warp roles (18 warps): warps 0-15 transform / epilogue in 4 groups of 4 warps -- thread == token row
+// == TMEM lane (lane quarter = warp % 4), group g owns columns [64g, 64g+64) in E1 / E2 and the
+// K-chunks {g, g+4} in the P2 / P3 feeds, so four chunks are produced concurrently and every SM
+// sub-partition has four transform warps to hide TMEM / global latency; warp 16 TMA producer;
+// warp 17 MMA issuer (+ TMEM allocator).
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
 
+#ifndef HMVIT_CHAIN_DBG    // bottleneck-hunting builds only (results are wrong): 1 no stores, 2 no weight TMA, 4 no MMA, 8 no residual loads
+#define HMVIT_CHAIN_DBG 0
+#endif
+
 namespace hmvit {
+
+#ifdef HMVIT_TS   // timeline instrumentation build: CTA 0 records clock64() at phase boundaries of its first tiles
+__device__ unsigned long long g_chain_ts[2][16][16];   // [role: 0 transform, 1 mma][tile][event]
+#define CHAIN_TS(role, tile, ev) do { if (blockIdx.x == 0 && (tile) < 16) g_chain_ts[role][tile][ev] = clock64(); } while (0)
+#else
+#define CHAIN_TS(role, tile, ev) do { } while (0)
+#endif
 
 struct ChainParams {
   int B, L, N;
@@ -39,29 +53,44 @@ struct ChainParams {
 
 struct ChainMaps {             // TMA tensor maps
   CUtensorMap o;               // attention output rows bf16 [B*L*N][256], box 64 x 128
-  CUtensorMap wa[2];           // bf16 [256][256], box 64 x 128
-  CUtensorMap w1[2];           // fp32 [256][256], box 32 x 128
+  CUtensorMap wa[2];           // bf16 [256][256], box 64 x 256
+  CUtensorMap w1[2];           // fp32 [256][256], box 32 x 256
   CUtensorMap w2[2];
 };
 
 struct ChainCfg {
   static constexpr int BM = 128;
-  static constexpr int CHUNK = 16384;                 // 128 rows x 128 B
+  static constexpr int CHUNK = 16384;                 // A chunk: 128 rows x 128 B
+  static constexpr int WSTAGE = 32768;                // weight stage: 256 output channels x 128 B of K
+  // NF must be 4: ring stage g belongs to transform group g (single producer per stage, generations in
+  // program order -- an mbarrier parity wait cannot tell generation k from k - 2).
   static constexpr int NF = 4;                        // tf32 A-chunk ring stages
-  static constexpr int NS = 4;                        // weight ring stages
+  static constexpr int NS = 2;                        // weight ring stages (32 KB each)
   static constexpr int AO_BYTES = 4 * CHUNK;          // O tile, bf16
-  static constexpr int SMEM_BYTES = AO_BYTES + NF * CHUNK + NS * CHUNK + 256 + 1024;
-  static constexpr int THREADS = 192;
+  static constexpr int PART_BYTES = 4 * 128 * 8;      // per-group partial LN statistics
+  static constexpr int SMEM_BYTES = AO_BYTES + NF * CHUNK + NS * WSTAGE + PART_BYTES + 256 + 1024;
+  static constexpr int NT = 512;                      // transform threads
+  static constexpr int THREADS = NT + 64;
 };
 
-__global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
+// combine four (mean, M2) partials over 64 values each -> (mean, rstd) over 256
+HMVIT_DEVINL float2 ln_combine(const float2* part, int row, float eps) {
+  const float2 p0 = part[row], p1 = part[128 + row], p2 = part[256 + row], p3 = part[384 + row];
+  const float mean = 0.25f * (p0.x + p1.x + p2.x + p3.x);
+  const float d0 = p0.x - mean, d1 = p1.x - mean, d2 = p2.x - mean, d3 = p3.x - mean;
+  const float m2 = p0.y + p1.y + p2.y + p3.y + 64.0f * (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3);
+  return make_float2(mean, rsqrtf(fmaxf(m2 * (1.0f / kC), 0.f) + eps));
+}
+
+__global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   using Cfg = ChainCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* sO = smem;
   uint8_t* sF = smem + Cfg::AO_BYTES;
   uint8_t* sW = sF + Cfg::NF * Cfg::CHUNK;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + Cfg::NS * Cfg::CHUNK);
+  float2* sPart = reinterpret_cast<float2*>(sW + Cfg::NS * Cfg::WSTAGE);  // [4 groups][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPart) + Cfg::PART_BYTES);
   uint64_t* w_full = bars;                      // [NS]
   uint64_t* w_empty = w_full + Cfg::NS;         // [NS]
   uint64_t* f_full = w_empty + Cfg::NS;         // [NF]
@@ -79,10 +108,10 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
     for (int s = 0; s < Cfg::NS; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     for (int s = 0; s < Cfg::NF; ++s) { mbar_init(&f_full[s], 128); mbar_init(&f_empty[s], 1); }
     mbar_init(o_full, 1); mbar_init(o_empty, 1);
-    mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d1_final, 1); mbar_init(d1_free, 128);
+    mbar_init(d1_full, 1); mbar_init(d2_full, 1); mbar_init(d1_final, 1); mbar_init(d1_free, Cfg::NT);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<512>(tmem_slot);
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -99,73 +128,93 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
     return l < p.record_len[b] && !(p.tile_ego_only && l != 0);
   };
 
-  if (warp < 4) {
+  if (warp < 16) {
     // ============================ transform / epilogue warps ============================
-    const int row = threadIdx.x;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    uint32_t ti = 0, itf = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    const int gq = warp >> 2;                          // column / chunk group
+    const int row = (warp & 3) * 32 + lane;            // token row == TMEM lane
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const int c0 = gq * 64;                            // first column owned in E1 / E2
+    uint32_t ti = 0;
+    auto next_valid = [&](int t) { int a_, k_; while (t < total_tiles && !tile_agent(t, a_, k_)) t += gridDim.x; return t; };
+    // L2 prefetch of the NEXT tile's residual rows (256 channel segments of 512 B): issued while this
+    // tile's FFN runs, so that the register loads at the start of the next tile hit L2 instead of HBM
+    auto prefetch_resid_l2 = [&](int tn) {
+      int a_, k_;
+      if (threadIdx.x < kC && tn < total_tiles && tile_agent(tn, a_, k_)) {
+        const float* r_ = p.resid_cm + (static_cast<size_t>(a_) * kC + threadIdx.x) * p.N + k_;
+        const uint32_t bytes = static_cast<uint32_t>(min(Cfg::BM, p.N - k_)) * 4u;
+        if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(r_) & 15u) == 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(r_), "r"(bytes) : "memory");
+      }
+    };
+    int t = next_valid(blockIdx.x);
+    while (t < total_tiles) {
+      const int t_next = next_valid(t + gridDim.x);
       int a, tok0;
-      if (!tile_agent(t, a, tok0)) continue;
+      tile_agent(t, a, tok0);
       const int type = p.mode[a] != 0 ? 1 : 0;
       const int tok = tok0 + row;
       const bool valid = tok < p.N;
       const size_t cm_off = static_cast<size_t>(a) * kC * p.N + (valid ? tok : 0);
-      const float* res = p.resid_cm + cm_off;
-      float* dst = p.out_cm + cm_off;
-      // ---- E1: x' = D1 + b_a + x ; statistics.  The residual loads run 3 pieces ahead and start
-      //      before the projection MMAs have finished. ----
-      float rv[3][32];
+      const float* res = p.resid_cm + cm_off + static_cast<size_t>(c0) * p.N;
+      float* dst = p.out_cm + cm_off + static_cast<size_t>(c0) * p.N;
+      // ---- E1: x' = D1 + b_a + x on this group's 64 columns; the residual loads are issued before the
+      //      projection MMAs have finished (and were L2-prefetched during the previous tile) ----
+      float rv[64];
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-#pragma unroll
-        for (int k = 0; k < 32; ++k) rv[q][k] = valid ? res[static_cast<size_t>(q * 32 + k) * p.N] : 0.f;
-      }
+      for (int k = 0; k < 64; ++k) rv[k] = (valid && !(HMVIT_CHAIN_DBG & 8)) ? res[static_cast<size_t>(k) * p.N] : 0.f;
+      if (threadIdx.x == 0) CHAIN_TS(0, ti, 0);
       mbar_wait(d1_full, ti & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) CHAIN_TS(0, ti, 1);
       float s0 = 0.f, sum = 0.f, sq = 0.f;
+      {
+        const float* bias = p.ba + type * kC + c0;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint32_t r[32];
-        tmem_ld32(D1 + lane_base + q * 32, r);
-        tmem_ld_wait();
-        const float* bias = p.ba + type * kC + q * 32;
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tmem_ld16(D1 + lane_base + c0 + q * 16, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float v = __uint_as_float(r[k]) + __ldg(bias + k) + rv[q % 3][k];
-          if (q == 0 && k == 0) s0 = v;
-          const float d = v - s0;
-          sum += d; sq += d * d;
-          r[k] = __float_as_uint(v);
-        }
-        tmem_st32(D1 + lane_base + q * 32, r);
-        if (q + 3 < 8) {
-#pragma unroll
-          for (int k = 0; k < 32; ++k) rv[q % 3][k] = valid ? res[static_cast<size_t>((q + 3) * 32 + k) * p.N] : 0.f;
+          for (int k = 0; k < 16; ++k) {
+            const float v = __uint_as_float(r[k]) + __ldg(bias + q * 16 + k) + rv[q * 16 + k];
+            if (q == 0 && k == 0) s0 = v;
+            const float d = v - s0;
+            sum += d; sq += d * d;
+            r[k] = __float_as_uint(v);
+            rv[q * 16 + k] = v;                    // x' stays in registers for the LayerNorm feed below
+          }
+          tmem_st16(D1 + lane_base + c0 + q * 16, r);
         }
       }
       tmem_st_wait();
-      const float md = sum * (1.0f / kC);
-      const float mean = s0 + md;
-      const float rstd = rsqrtf(fmaxf(sq * (1.0f / kC) - md * md, 0.f) + p.ln_eps);
-      // ---- P2 feed: LN'(x') -> tf32 K-chunks ----
+      {
+        const float md = sum * (1.0f / 64.0f);
+        sPart[gq * 128 + row] = make_float2(s0 + md, fmaxf(sq - sum * md, 0.f));     // (mean_g, M2_g)
+      }
+      tc_fence_before();
+      named_bar_sync(1, Cfg::NT);
+      tc_fence_after();
+      const float2 st = ln_combine(sPart, row, p.ln_eps);
+      const float rstd = st.y, nmr = -st.x * st.y;
+      if (threadIdx.x == 0) CHAIN_TS(0, ti, 2);
+      // ---- P2 feed: LN'(x') -> tf32 K-chunks kc = 2gq, 2gq + 1 (this group's own columns, from registers) ----
       const bool affine = p.ln_gamma != nullptr;
       const float* gam = affine ? p.ln_gamma + type * kC : nullptr;
       const float* bet = affine ? p.ln_beta + type * kC : nullptr;
-      const float nmr = -mean * rstd;
-#pragma unroll 1
-      for (int kc = 0; kc < 8; ++kc, ++itf) {
-        const uint32_t fs = itf % Cfg::NF, ph = (itf / Cfg::NF) & 1u;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int kc = 2 * gq + kk;
+        // ring stage gq belongs to this group (single producer): 4 generations per tile (P2: 2, P3: 2)
+        const uint32_t fs = gq, ph = (ti * 4 + kk) & 1u;
         uint32_t r[32];
-        tmem_ld32(D1 + lane_base + kc * 32, r);
-        tmem_ld_wait();
         if (affine) {
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            r[k] = __float_as_uint(tf32_rn(fmaf(__uint_as_float(r[k]), rstd, nmr) * __ldg(gam + kc * 32 + k) + __ldg(bet + kc * 32 + k)));
+            r[k] = __float_as_uint(tf32_rn(fmaf(rv[kk * 32 + k], rstd, nmr) * __ldg(gam + kc * 32 + k) + __ldg(bet + kc * 32 + k)));
         } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(tf32_rn(fmaf(__uint_as_float(r[k]), rstd, nmr)));
+          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(tf32_rn(fmaf(rv[kk * 32 + k], rstd, nmr)));
         }
         mbar_wait(&f_empty[fs], ph ^ 1u);
         uint8_t* dstF = sF + fs * Cfg::CHUNK;
@@ -176,13 +225,17 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
         tc_fence_before();
         mbar_arrive(&f_full[fs]);
       }
-      // ---- P3 feed: gelu(D2 + b_1) -> tf32 K-chunks ----
+      prefetch_resid_l2(t_next);
+      // ---- P3 feed: gelu(D2 + b_1) -> tf32 K-chunks kc = 2gq, 2gq + 1 ----
+      if (threadIdx.x == 0) CHAIN_TS(0, ti, 3);
       mbar_wait(d2_full, ti & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) CHAIN_TS(0, ti, 4);
       const float* b1 = p.b1 + type * kC;
 #pragma unroll 1
-      for (int kc = 0; kc < 8; ++kc, ++itf) {
-        const uint32_t fs = itf % Cfg::NF, ph = (itf / Cfg::NF) & 1u;
+      for (int kk = 0; kk < 2; ++kk) {
+        const int kc = 2 * gq + kk;
+        const uint32_t fs = gq, ph = (ti * 4 + 2 + kk) & 1u;
         uint32_t r[32];
         tmem_ld32(D2 + lane_base + kc * 32, r);
         tmem_ld_wait();
@@ -197,35 +250,42 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
         tc_fence_before();
         mbar_arrive(&f_full[fs]);
       }
-      // ---- E2: x'' = D1 + b_2 (+ LayerNorm statistics of x'' for the next stage) ----
+      // ---- E2: x'' = D1 + b_2 on this group's 64 columns (+ LayerNorm statistics of x'') ----
+      if (threadIdx.x == 0) CHAIN_TS(0, ti, 5);
       mbar_wait(d1_final, ti & 1);
       tc_fence_after();
-      const float* b2 = p.b2 + type * kC;
+      if (threadIdx.x == 0) CHAIN_TS(0, ti, 6);
+      const float* b2 = p.b2 + type * kC + c0;
       float t0 = 0.f, tsum = 0.f, tsq = 0.f;
-#pragma unroll 1
-      for (int q = 0; q < 8; ++q) {
-        uint32_t r[32];
-        tmem_ld32(D1 + lane_base + q * 32, r);
+      {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(D1 + lane_base + c0, r0);
+        tmem_ld32(D1 + lane_base + c0 + 32, r1);
         tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(d1_free);                      // D1 is in registers: the next tile's projection may start
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float v = __uint_as_float(r[k]) + __ldg(b2 + q * 32 + k);
-          if (q == 0 && k == 0) t0 = v;
+        for (int k = 0; k < 64; ++k) {
+          const float v = __uint_as_float(k < 32 ? r0[k] : r1[k - 32]) + __ldg(b2 + k);
+          if (k == 0) t0 = v;
           const float d = v - t0;
           tsum += d; tsq += d * d;
-          if (valid) dst[static_cast<size_t>(q * 32 + k) * p.N] = v;
+          if (valid && (!(HMVIT_CHAIN_DBG & 1) || v == 12345.678f)) dst[static_cast<size_t>(k) * p.N] = v;
         }
       }
-      if (p.stats_out != nullptr && valid) {
-        const float tmd = tsum * (1.0f / kC);
-        p.stats_out[static_cast<size_t>(a) * p.N + tok] =
-            make_float2(t0 + tmd, rsqrtf(fmaxf(tsq * (1.0f / kC) - tmd * tmd, 0.f) + p.ln_eps));
+      if (threadIdx.x == 0) CHAIN_TS(0, ti, 7);
+      if (p.stats_out != nullptr) {
+        const float tmd = tsum * (1.0f / 64.0f);
+        sPart[gq * 128 + row] = make_float2(t0 + tmd, fmaxf(tsq - tsum * tmd, 0.f));
+        named_bar_sync(1, Cfg::NT);
+        if (gq == 0 && valid) p.stats_out[static_cast<size_t>(a) * p.N + tok] = ln_combine(sPart, row, p.ln_eps);
+        named_bar_sync(1, Cfg::NT);     // sPart is rewritten by the next tile's E1
       }
-      tc_fence_before();
-      mbar_arrive(d1_free);
+      if (threadIdx.x == 0) CHAIN_TS(0, ti, 8);
       ++ti;
+      t = t_next;
     }
-  } else if (warp == 4) {
+  } else if (warp == 16) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       tma_prefetch_desc(&maps.o);
@@ -238,71 +298,73 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
         mbar_arrive_expect_tx(o_full, Cfg::AO_BYTES);
         const int row0 = a * p.N + tok0;
         for (int kc = 0; kc < 4; ++kc) tma_load_2d(sO + kc * Cfg::CHUNK, &maps.o, o_full, kc * 64, row0);
-        auto wstage = [&](const CUtensorMap* m, int c0, int c1) {
+        auto wstage = [&](const CUtensorMap* m, int c0) {
           const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
           mbar_wait(&w_empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&w_full[s], Cfg::CHUNK);
-          tma_load_2d(sW + s * Cfg::CHUNK, m, &w_full[s], c0, c1);
+          if ((HMVIT_CHAIN_DBG & 2) && itw >= Cfg::NS) { mbar_arrive(&w_full[s]); ++itw; return; }
+          mbar_arrive_expect_tx(&w_full[s], Cfg::WSTAGE);
+          tma_load_2d(sW + s * Cfg::WSTAGE, m, &w_full[s], c0, 0);
           ++itw;
         };
-        for (int nc = 0; nc < 2; ++nc)
-          for (int kc = 0; kc < 4; ++kc) wstage(&maps.wa[type], kc * 64, nc * 128);
-        for (int kc = 0; kc < 8; ++kc)
-          for (int nc = 0; nc < 2; ++nc) wstage(&maps.w1[type], kc * 32, nc * 128);
-        for (int kc = 0; kc < 8; ++kc)
-          for (int nc = 0; nc < 2; ++nc) wstage(&maps.w2[type], kc * 32, nc * 128);
+        for (int kc = 0; kc < 4; ++kc) wstage(&maps.wa[type], kc * 64);
+        for (int j = 0; j < 8; ++j) wstage(&maps.w1[type], (2 * (j & 3) + (j >> 2)) * 32);   // same order as the MMA issuer
+        for (int j = 0; j < 8; ++j) wstage(&maps.w2[type], (2 * (j & 3) + (j >> 2)) * 32);
         ++ti;
       }
     }
   } else {
     // ============================ MMA issuer ============================
     if (lane == 0) {
-      constexpr uint32_t idesc_bf16 = umma_idesc(1u, 128, 128);
-      constexpr uint32_t idesc_tf32 = umma_idesc(2u, 128, 128);
+      constexpr uint32_t idesc_bf16 = umma_idesc(1u, 128, 256);
+      constexpr uint32_t idesc_tf32 = umma_idesc(2u, 128, 256);
       const uint32_t o_base = smem_u32(sO), f_base = smem_u32(sF), w_base = smem_u32(sW);
-      uint32_t ti = 0, itw = 0, itf = 0;
+      uint32_t ti = 0, itw = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int a, tok0;
         if (!tile_agent(t, a, tok0)) continue;
+        CHAIN_TS(1, ti, 0);
         mbar_wait(d1_free, (ti & 1) ^ 1u);
+        CHAIN_TS(1, ti, 1);
         mbar_wait(o_full, ti & 1);
         tc_fence_after();
-        // P1: D1 = O W_a^T
-        for (int nc = 0; nc < 2; ++nc) {
-          for (int kc = 0; kc < 4; ++kc, ++itw) {
-            const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
-            mbar_wait(&w_full[s], ph);
-            tc_fence_after();
+        CHAIN_TS(1, ti, 2);
+        // P1: D1 = O W_a^T   (4 weight stages of 64 K-columns, one M128 N256 K16 MMA per k-step)
+        for (int kc = 0; kc < 4; ++kc, ++itw) {
+          const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
+          mbar_wait(&w_full[s], ph);
+          tc_fence_after();
+          if (!(HMVIT_CHAIN_DBG & 4))
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ss<2>(D1 + nc * 128, umma_desc_sw128(o_base + kc * Cfg::CHUNK + ks * 32),
-                         umma_desc_sw128(w_base + s * Cfg::CHUNK + ks * 32), idesc_bf16, (kc | ks) != 0 ? 1u : 0u);
-            umma_commit(&w_empty[s]);
-          }
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss<2>(D1, umma_desc_sw128(o_base + kc * Cfg::CHUNK + ks * 32),
+                       umma_desc_sw128(w_base + s * Cfg::WSTAGE + ks * 32), idesc_bf16, (kc | ks) != 0 ? 1u : 0u);
+          umma_commit(&w_empty[s]);
         }
         umma_commit(o_empty);
         umma_commit(d1_full);
-        // P2: D2 = LN'(x') W_1^T      P3: D1 += gelu(.) W_2^T
+        CHAIN_TS(1, ti, 3);
+        // P2: D2 = LN'(x') W_1^T      P3: D1 += gelu(.) W_2^T     (8 stages of 32 K-columns each)
         for (int phase = 0; phase < 2; ++phase) {
           const uint32_t dacc = phase == 0 ? D2 : D1;
-          for (int kc = 0; kc < 8; ++kc, ++itf) {
-            const uint32_t fs = itf % Cfg::NF, fph = (itf / Cfg::NF) & 1u;
+          // K-chunks are consumed first-chunk-of-every-group first (j -> group j % 4, sub-chunk j / 4 of that
+          // group), the order in which the four transform groups finish them; accumulation order is free
+          for (int j = 0; j < 8; ++j, ++itw) {
+            const uint32_t fs = j & 3, fph = (ti * 4 + phase * 2 + (j >> 2)) & 1u;
+            const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
             mbar_wait(&f_full[fs], fph);
+            mbar_wait(&w_full[s], ph);
             tc_fence_after();
-            for (int nc = 0; nc < 2; ++nc, ++itw) {
-              const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
-              mbar_wait(&w_full[s], ph);
-              tc_fence_after();
+            if (!(HMVIT_CHAIN_DBG & 4))
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_ss<4>(dacc + nc * 128, umma_desc_sw128(f_base + fs * Cfg::CHUNK + ks * 32),
-                           umma_desc_sw128(w_base + s * Cfg::CHUNK + ks * 32), idesc_tf32,
-                           (phase == 1 || (kc | ks) != 0) ? 1u : 0u);
-              umma_commit(&w_empty[s]);
-            }
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss<4>(dacc, umma_desc_sw128(f_base + fs * Cfg::CHUNK + ks * 32),
+                         umma_desc_sw128(w_base + s * Cfg::WSTAGE + ks * 32), idesc_tf32,
+                         (phase == 1 || (j | ks) != 0) ? 1u : 0u);
+            umma_commit(&w_empty[s]);
             umma_commit(&f_empty[fs]);
           }
           umma_commit(phase == 0 ? d2_full : d1_final);
+          CHAIN_TS(1, ti, 4 + phase);
         }
         ++ti;
       }
@@ -311,7 +373,7 @@ __global__ void __launch_bounds__(192, 1) chain_kernel(const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 17) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

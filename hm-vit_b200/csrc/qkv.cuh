@@ -38,10 +38,19 @@ struct QkvCfg {
   static constexpr int BM = 128, BN = 128;
   static constexpr int CHUNK = 16384;
   static constexpr int NCHA = 4;                       // A chunks (bf16, K = 256)
-  static constexpr int NS = 3;                         // weight ring stages
+#ifndef HMVIT_QKV_NS
+#define HMVIT_QKV_NS 5
+#endif
+#ifndef HMVIT_QKV_ROT
+#define HMVIT_QKV_ROT 1
+#endif
+#ifndef HMVIT_QKV_DBG      // bottleneck-hunting builds only (results are wrong): 1 no stores, 2 no weight TMA, 4 no MMA, 8 no x loads
+#define HMVIT_QKV_DBG 0
+#endif
+  static constexpr int NS = HMVIT_QKV_NS;              // weight ring stages
   static constexpr int N_CHUNKS = 10;                  // 1280 / 128
   static constexpr int A_BYTES = NCHA * CHUNK;         // 64 KB per A buffer
-  static constexpr int STAGE_BYTES = 4 * 32 * 256;     // epilogue staging: 4 warps x 32 rows x 256 B
+  static constexpr int STAGE_BYTES = 4 * 32 * 128;     // epilogue staging: 4 warps x 32 rows x 128 B (64 columns)
   static constexpr int SMEM_BYTES = 2 * A_BYTES + NS * CHUNK + STAGE_BYTES + 256 + 1024;
   static constexpr int THREADS = 320;
   static constexpr uint32_t TMEM_COLS = 256;
@@ -101,53 +110,64 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
     return true;
   };
 
+  // CTAs walk the 10 weight chunks in a rotated order so that the 148 SMs do not all stream the same
+  // L2 lines at the same time
+  const int rot = HMVIT_QKV_ROT ? static_cast<int>(blockIdx.x % Cfg::N_CHUNKS) : 0;
+
   if (warp < 4) {
     // ============================ epilogue ============================
     const int row = threadIdx.x;
     const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    uint8_t* stg = sStage + warp * (32 * 256);
+    uint8_t* stg = sStage + warp * (32 * 128);
     const size_t rows_total = static_cast<size_t>(p.B) * p.L * p.N;
     uint32_t ci = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int a, tok0; uint32_t chunk_mask;
       if (!tile_info(t, a, tok0, chunk_mask)) continue;
       const int type = p.mode[a] != 0 ? 1 : 0;
-      for (int c = 0; c < Cfg::N_CHUNKS; ++c) {
+      for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
+        const int c = (cc + rot) % Cfg::N_CHUNKS;
         if (!((chunk_mask >> c) & 1u)) continue;
         const uint32_t buf = ci & 1u;
         mbar_wait(&acc_full[buf], (ci >> 1) & 1u);
         tc_fence_after();
         const float* bias = p.bias + type * (Cfg::N_CHUNKS * Cfg::BN) + c * Cfg::BN;
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + q * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int k8 = 0; k8 < 4; ++k8) {
-            const float* bb = bias + q * 32 + k8 * 8;
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(r[k8 * 8 + 0]) + __ldg(bb + 0), __uint_as_float(r[k8 * 8 + 1]) + __ldg(bb + 1));
-            pk.y = pack_bf16x2(__uint_as_float(r[k8 * 8 + 2]) + __ldg(bb + 2), __uint_as_float(r[k8 * 8 + 3]) + __ldg(bb + 3));
-            pk.z = pack_bf16x2(__uint_as_float(r[k8 * 8 + 4]) + __ldg(bb + 4), __uint_as_float(r[k8 * 8 + 5]) + __ldg(bb + 5));
-            pk.w = pack_bf16x2(__uint_as_float(r[k8 * 8 + 6]) + __ldg(bb + 6), __uint_as_float(r[k8 * 8 + 7]) + __ldg(bb + 7));
-            const int u = q * 4 + k8;
-            *reinterpret_cast<uint4*>(stg + lane * 256 + ((u ^ (lane & 7)) << 4)) = pk;
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);           // TMEM buffer drained: the MMA warp may refill it
-        __syncwarp();
-        // coalesced stores: 2 rows (2 x 256 B) per instruction
         __nv_bfloat16* obase = p.out_rows + (static_cast<size_t>(c >> 1) * rows_total + static_cast<size_t>(a) * p.N + tok0 + warp * 32) * kC +
                                (c & 1) * Cfg::BN;
-#pragma unroll 4
-        for (int it = 0; it < 16; ++it) {
-          const int rr = it * 2 + (lane >> 4), u = lane & 15;
-          const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 256 + ((u ^ (rr & 7)) << 4));
-          if (tok0 + warp * 32 + rr < p.N) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * kC + u * 8) = v;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + half * 64, r0);
+          tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + half * 64 + 32, r1);
+          tmem_ld_wait();
+          if (half == 1) {                        // both halves are in registers: the MMA warp may refill the buffer
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+          }
+          const float* bb = bias + half * 64;
+#pragma unroll
+          for (int k8 = 0; k8 < 8; ++k8) {
+            const uint32_t* r = (k8 < 4) ? (r0 + k8 * 8) : (r1 + (k8 - 4) * 8);
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bb + k8 * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bb + k8 * 8 + 4));
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(r[0]) + b0.x, __uint_as_float(r[1]) + b0.y);
+            pk.y = pack_bf16x2(__uint_as_float(r[2]) + b0.z, __uint_as_float(r[3]) + b0.w);
+            pk.z = pack_bf16x2(__uint_as_float(r[4]) + b1.x, __uint_as_float(r[5]) + b1.y);
+            pk.w = pack_bf16x2(__uint_as_float(r[6]) + b1.z, __uint_as_float(r[7]) + b1.w);
+            *reinterpret_cast<uint4*>(stg + lane * 128 + ((k8 ^ (lane & 7)) << 4)) = pk;
+          }
+          __syncwarp();
+          // coalesced stores: 4 rows x 128 B per instruction
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), u = lane & 7;
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((u ^ (rr & 7)) << 4));
+            if (!(HMVIT_QKV_DBG & 1) || v.x == 0x12345678u)
+            if (tok0 + warp * 32 + rr < p.N) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * kC + half * 64 + u * 8) = v;
+          }
+          __syncwarp();
         }
-        __syncwarp();
         ++ci;
       }
     }
@@ -161,11 +181,13 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         int a, tok0; uint32_t chunk_mask;
         if (!tile_info(t, a, tok0, chunk_mask)) continue;
         const CUtensorMap* tmap = (p.mode[a] != 0) ? &tmap1 : &tmap0;
-        for (int c = 0; c < Cfg::N_CHUNKS; ++c) {
+        for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
+          const int c = (cc + rot) % Cfg::N_CHUNKS;
           if (!((chunk_mask >> c) & 1u)) continue;
           for (int kc = 0; kc < Cfg::NCHA; ++kc, ++it) {
             const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
             mbar_wait(&b_empty[s], ph ^ 1u);
+            if ((HMVIT_QKV_DBG & 2) && it >= Cfg::NS) { mbar_arrive(&b_full[s]); continue; }
             mbar_arrive_expect_tx(&b_full[s], Cfg::CHUNK);
             tma_load_2d(sB + s * Cfg::CHUNK, tmap, &b_full[s], kc * 64, c * Cfg::BN);
           }
@@ -185,7 +207,8 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         mbar_wait(&a_full[ab], (ti >> 1) & 1u);
         tc_fence_after();
         const uint32_t a_base = a_base0 + ab * Cfg::A_BYTES;
-        for (int c = 0; c < Cfg::N_CHUNKS; ++c) {
+        for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
+          const int c = (cc + rot) % Cfg::N_CHUNKS;
           if (!((chunk_mask >> c) & 1u)) continue;
           const uint32_t buf = ci & 1u;
           mbar_wait(&acc_empty[buf], ((ci >> 1) & 1u) ^ 1u);
@@ -195,10 +218,12 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
             const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
             mbar_wait(&b_full[s], ph);
             tc_fence_after();
+            if (!(HMVIT_QKV_DBG & 4)) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_ss<2>(d_tmem, umma_desc_sw128(a_base + kc * Cfg::CHUNK + ks * 32),
-                         umma_desc_sw128(b_base + s * Cfg::CHUNK + ks * 32), idesc, (kc | ks) != 0 ? 1u : 0u);
+              for (int ks = 0; ks < 4; ++ks)
+                umma_ss<2>(d_tmem, umma_desc_sw128(a_base + kc * Cfg::CHUNK + ks * 32),
+                           umma_desc_sw128(b_base + s * Cfg::CHUNK + ks * 32), idesc, (kc | ks) != 0 ? 1u : 0u);
+            }
             umma_commit(&b_empty[s]);
           }
           umma_commit(&acc_full[buf]);
@@ -250,7 +275,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
       for (int c0 = 0; c0 < kC; c0 += 64) {
         float xv[64];
 #pragma unroll
-        for (int e = 0; e < 64; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+        for (int e = 0; e < 64; ++e) xv[e] = (valid && !(HMVIT_QKV_DBG & 8)) ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
         if constexpr (kLN) {
           if (affine) {
 #pragma unroll
