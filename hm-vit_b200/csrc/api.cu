@@ -204,6 +204,10 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
     attr_err = cudaFuncSetAttribute(group_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+#ifdef HMVIT_ATTN_CARVEOUT
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(group_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, HMVIT_ATTN_CARVEOUT);
+#endif
   });
   HMVIT_CHECK_CUDA(attr_err);
   AttnParams p;
@@ -403,6 +407,10 @@ extern "C" int hmvit_debug_probe(uint32_t* out2, void* stream) {
 }
 
 #ifdef HMVIT_TS
+extern "C" int hmvit_debug_attn_ts(unsigned long long* host_out /* [8][8][4] */) {
+  HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_attn_ts, sizeof(unsigned long long) * 8 * 8 * 4));
+  return HMVIT_OK;
+}
 extern "C" int hmvit_debug_chain_ts(unsigned long long* host_out /* [2][16][16] */) {
   HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_chain_ts, sizeof(unsigned long long) * 2 * 16 * 16));
   return HMVIT_OK;

@@ -20,6 +20,13 @@
 
 namespace hmvit {
 
+#ifdef HMVIT_TS
+__device__ unsigned long long g_attn_ts[8][8][4];   // [cta sample][source][event]
+#define ATTN_TS(j, ev) do { if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < 8) g_attn_ts[blockIdx.x][j][ev] = clock64(); } while (0)
+#else
+#define ATTN_TS(j, ev) do { } while (0)
+#endif
+
 struct AttnParams {
   int B, L, H, W;
   int kind;                    // 0 = window partition, 1 = grid partition
@@ -130,6 +137,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
 
   for (int j = 0; j < nrec; ++j) {
     if (p.cav_mask[b * p.L + j] == 0) continue;
+    ATTN_TS(j, 0);
     // ---- taps + visibility for the 64 tokens of this group, source j -> ego i ----
     int vis = 0;
     if (threadIdx.x < kS) {
@@ -144,6 +152,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
       sTap[threadIdx.x] = rec;
     }
     if (!__syncthreads_or(vis)) continue;      // source invisible in this group: its softmax weight is exactly 0
+    ATTN_TS(j, 1);
 
     // ---- gather projected K / V rows of source j: 4-tap blend with packed bf16 FMAs, + folded bias ----
     {
@@ -191,6 +200,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
       }
     }
     __syncthreads();
+    ATTN_TS(j, 2);
 
     // ---- key visibility bits for this thread's columns: key s' = nt*8 + 2t + e -> bit nt*2 + e ----
     uint32_t vbits = 0;
@@ -282,6 +292,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
       }
     }
     __syncthreads();     // compute phase done before sTap / sK / sV are rewritten for the next source
+    ATTN_TS(j, 3);
   }
 
   // ---- normalise, stage in smem (reuse sK), coalesced store ----

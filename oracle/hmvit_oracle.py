@@ -394,3 +394,66 @@ def synth_inputs(B: int, L: int, C: int, H: int, W: int, record_len, seed: int, 
         mode = torch.as_tensor(mode, dtype=torch.int32).clone()
     mode = mode * mask.to(torch.int32)                                      # padded slots are camera (0)
     return x, T.to(torch.float32), mode, record_len, mask
+
+
+# --------------------------------------------------------------------------
+# detection heads after the fusion (test infrastructure for the "logits" parity row)
+# --------------------------------------------------------------------------
+def decoder_state_spec(input_dim: int = 256, num_layer: int = 2, num_ch_dec=(256, 256), anchor_number: int = 2):
+    """(key, shape) list of HeteroDecoder.state_dict() (hetero_decoder.py:27-40, naive_decoder.py:27-54):
+    per modality 2 x (conv3x3-BN-ReLU, conv3x3-BN-ReLU) + 1x1 cls / reg heads."""
+    spec = []
+    for mod in ("camera", "lidar"):
+        idx = 0
+        for i in range(num_layer - 1, -1, -1):
+            cin = input_dim if i == num_layer - 1 else num_ch_dec[i + 1]
+            cout = num_ch_dec[i]
+            for c_in in (cin, cout):
+                spec.append((f"{mod}_decoder.decoder.{idx}.weight", (cout, c_in, 3, 3)))
+                spec.append((f"{mod}_decoder.decoder.{idx}.bias", (cout,)))
+                for nm, shp in (("weight", (cout,)), ("bias", (cout,)), ("running_mean", (cout,)),
+                                ("running_var", (cout,)), ("num_batches_tracked", ())):
+                    spec.append((f"{mod}_decoder.decoder.{idx + 1}.{nm}", shp))
+                idx += 3
+    for mod in ("camera", "lidar"):
+        spec.append((f"{mod}_cls_head.weight", (anchor_number, num_ch_dec[0], 1, 1)))
+        spec.append((f"{mod}_cls_head.bias", (anchor_number,)))
+        spec.append((f"{mod}_reg_head.weight", (7 * anchor_number, num_ch_dec[0], 1, 1)))
+        spec.append((f"{mod}_reg_head.bias", (7 * anchor_number,)))
+    return spec
+
+
+def synth_decoder_state_dict(seed: int = 0, **kw) -> Dict[str, Tensor]:
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    for key, shape in decoder_state_spec(**kw):
+        if key.endswith("num_batches_tracked"):
+            P[key] = torch.tensor(0, dtype=torch.int64)
+        elif key.endswith("running_var"):
+            P[key] = 0.5 + torch.rand(shape, generator=g)
+        elif key.endswith("running_mean") or key.endswith("bias"):
+            P[key] = 0.1 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:                       # BN weight
+            P[key] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:                                       # conv weight
+            fan_in = shape[1] * shape[2] * shape[3]
+            P[key] = torch.randn(shape, generator=g) / math.sqrt(fan_in)
+    return P
+
+
+def hetero_decoder(x: Tensor, ego_mode: Tensor, P: Dict[str, Tensor], num_layer: int = 2):
+    """HeteroDecoder.forward with use_upsample=False, eval-mode BatchNorm (hetero_decoder.py:42-74,
+    naive_decoder.py:63-92): x (B, C, H, W) fused ego feature, ego_mode (B,) -> psm (B, A, H, W), rm (B, 7A, H, W)."""
+    psm, rm = [], []
+    for b in range(x.shape[0]):
+        mod = "lidar" if int(ego_mode[b]) == 1 else "camera"
+        y = x[b:b + 1]
+        for blk in range(2 * num_layer):
+            i = 3 * blk
+            y = F.conv2d(y, P[f"{mod}_decoder.decoder.{i}.weight"], P[f"{mod}_decoder.decoder.{i}.bias"], padding=1)
+            y = F.batch_norm(y, P[f"{mod}_decoder.decoder.{i + 1}.running_mean"], P[f"{mod}_decoder.decoder.{i + 1}.running_var"],
+                             P[f"{mod}_decoder.decoder.{i + 1}.weight"], P[f"{mod}_decoder.decoder.{i + 1}.bias"], False, 0.0, 1e-5)
+            y = F.relu(y)
+        psm.append(F.conv2d(y, P[f"{mod}_cls_head.weight"], P[f"{mod}_cls_head.bias"]))
+        rm.append(F.conv2d(y, P[f"{mod}_reg_head.weight"], P[f"{mod}_reg_head.bias"]))
+    return torch.cat(psm, 0), torch.cat(rm, 0)

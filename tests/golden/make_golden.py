@@ -111,6 +111,26 @@ def gen_index(R):
     print("index ok")
 
 
+def gen_logits(R):
+    """Detection-head logits of the reference pipeline: HeteroFusion -> HeteroDecoder (eval-mode BN,
+    use_upsample=False) on the fusion_c256 case (hetero_decoder.py:42-74)."""
+    C, B, L, H, W, rl, seed, tx, ty = CASES_FUSION["fusion_c256"]
+    cfg = O.default_config(input_dim=C)
+    P = O.synth_state_dict(cfg, seed)
+    PD = O.synth_decoder_state_dict(seed + 1)
+    x, T, mode, record_len, mask = O.synth_inputs(B, L, C, H, W, rl, seed + 100, tx=tx, ty=ty)
+    ref = R.HeteroFusion(cfg).eval()
+    ref.load_state_dict(P, strict=True)
+    dec = R.HeteroDecoder({"input_dim": 256, "num_layer": 2, "num_ch_dec": [256, 256], "anchor_number": 2}).eval()
+    dec.load_state_dict(PD, strict=True)
+    with torch.no_grad():
+        fused = ref(x.clone(), T.clone(), mode.clone(), record_len.clone(), mask.clone())
+        psm, rm = dec(fused.unsqueeze(1), mode, use_upsample=False)
+    np.savez_compressed(os.path.join(HERE, "logits_c256.npz"), psm=psm.numpy(), rm=rm.numpy(),
+                        pd_checksum=np.array([sum(checksum(v.float()) for v in PD.values())]))
+    print("logits", tuple(psm.shape), tuple(rm.shape), "ok")
+
+
 if __name__ == "__main__":
     R = ref_import.load()
     torch.manual_seed(0)
@@ -118,3 +138,4 @@ if __name__ == "__main__":
     gen_warp_mask(R)
     gen_attention(R)
     gen_fusion(R)
+    gen_logits(R)

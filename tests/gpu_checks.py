@@ -335,6 +335,37 @@ def check_fusion_golden():
     return res
 
 
+def check_logits_golden():
+    """Detection-head logits: CUDA fused feature -> decoder restatement (CPU, eval-mode BN) against the
+    reference pipeline's psm / rm (tests/golden/logits_c256.npz).  Tolerance 1e-3 rel-L2 per tensor."""
+    g = np.load(os.path.join(GOLDEN, "fusion_c256.npz"))
+    gl = np.load(os.path.join(GOLDEN, "logits_c256.npz"))
+    C, B, L, H, W, seed = (int(v) for v in g["meta"][:6])
+    cfg = O.default_config(input_dim=C)
+    P = O.synth_state_dict(cfg, seed)
+    PD = O.synth_decoder_state_dict(seed + 1)
+    x, T, mode, rl, mask = O.synth_inputs(B, L, C, H, W, g["record_len"].tolist(), seed + 100,
+                                          tx=float(g["meta"][6]), ty=float(g["meta"][7]))
+    net = pkg().HeteroFusion(cfg).eval()
+    net.load_state_dict(P, strict=True)
+    net = net.to(DEV)
+    with torch.no_grad():
+        y = net(x.to(DEV), T.to(DEV), mode.to(DEV), rl.to(DEV), mask.to(DEV)).cpu()
+    psm, rm = O.hetero_decoder(y, mode[:, 0], PD)
+    res = {"psm_rel_l2": rel_l2(psm, torch.from_numpy(gl["psm"])), "rm_rel_l2": rel_l2(rm, torch.from_numpy(gl["rm"]))}
+    assert res["psm_rel_l2"] < 1e-3 and res["rm_rel_l2"] < 1e-3, res
+    return res
+
+
+def check_fusion_config5_scene():
+    """BASELINE config 5 shape, one scene: 7 agents (LiDAR ego + 6 camera collaborators), 256x96x352."""
+    cfg, P, inp, y, net = _fusion_case(1, 7, 96, 352, [7], seed=1239, mode=[[1, 0, 0, 0, 0, 0, 0]], tx=100.0, ty=30.0)
+    ref = O.hetero_fusion(*inp, P, cfg)
+    res = {"rel_l2_vs_oracle": rel_l2(y, ref), "max_rel_vs_oracle": max_rel(y, ref)}
+    assert res["rel_l2_vs_oracle"] < 1e-3, res
+    return res
+
+
 def check_fusion_config1():
     """BASELINE config 1: 2 agents (LiDAR ego + camera collaborator), 256x48x176, batch 1."""
     cfg, P, inp, y, net = _fusion_case(1, 2, 48, 176, [2], seed=1235, mode=[[1, 0]])
@@ -439,8 +470,10 @@ CHECKS = {
     "attention_golden": check_attention_golden,
     "fusion_small": check_fusion_small,
     "fusion_golden": check_fusion_golden,
+    "logits_golden": check_logits_golden,
     "fusion_config1": check_fusion_config1,
     "fusion_config2_scene": check_fusion_config2_scene,
     "fusion_properties": check_fusion_properties,
+    "fusion_config5_scene": check_fusion_config5_scene,
     "errors": check_errors,
 }

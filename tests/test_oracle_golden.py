@@ -98,6 +98,24 @@ def test_fusion_vs_reference_golden(name):
         assert rel_l2(blk[b], ref_blk[b]) < 1e-5
 
 
+def test_decoder_logits_vs_reference_golden():
+    """fusion (oracle) -> decoder restatement == reference fusion -> reference HeteroDecoder."""
+    g = np.load(os.path.join(GOLDEN, "fusion_c256.npz"))
+    gl = np.load(os.path.join(GOLDEN, "logits_c256.npz"))
+    C, B, L, H, W, seed = (int(v) for v in g["meta"][:6])
+    cfg = O.default_config(input_dim=C)
+    P = O.synth_state_dict(cfg, seed)
+    PD = O.synth_decoder_state_dict(seed + 1)
+    assert sum(checksum(v.float()) for v in PD.values()) == pytest.approx(float(gl["pd_checksum"][0]), rel=1e-9)
+    x, T, mode, record_len, mask = O.synth_inputs(B, L, C, H, W, g["record_len"].tolist(), seed + 100,
+                                                  tx=float(g["meta"][6]), ty=float(g["meta"][7]))
+    psm, rm = O.hetero_decoder(torch.from_numpy(g["fused"]), mode[:, 0], PD)
+    assert rel_l2(psm, torch.from_numpy(gl["psm"])) < 1e-5 and rel_l2(rm, torch.from_numpy(gl["rm"])) < 1e-5
+    fused = O.hetero_fusion(x, T, mode, record_len, mask, P, cfg)
+    psm2, rm2 = O.hetero_decoder(fused, mode[:, 0], PD)
+    assert rel_l2(psm2, torch.from_numpy(gl["psm"])) < 1e-5 and rel_l2(rm2, torch.from_numpy(gl["rm"])) < 1e-5
+
+
 def test_state_dict_spec_matches_default_module_keys():
     spec = O.state_dict_spec(O.default_config())
     keys = [k for k, _ in spec]
