@@ -49,8 +49,11 @@ struct AttnParams {
 constexpr int kAttnThreads = 256;
 constexpr int kTileBytes = kS * kC * 2;          // 32 KB: 64 tokens x 256 ch bf16
 constexpr int kBiasStride = 232;                 // [8 heads][225 (+7 pad)]
-struct TapRec { int x0, y0; float w00, w01, w10, w11; int vis; int pad; };
-constexpr int kAttnSmem = 3 * kTileBytes + kHeads * kBiasStride * 4 + kS * sizeof(TapRec);
+// per (source, token) gather record, 16 bytes: corner (x0, y0), visibility, 4 tap weights already
+// duplicated into bf16x2 pairs (the blend runs on packed bf16 FMAs)
+struct TapRec { short x0, y0; int vis; uint32_t w01; uint32_t w23; };   // w01 = (w00, w01) bf16 pair, w23 = (w10, w11)
+constexpr int kMaxSrc = 8;                       // sources handled per tap pass (L <= 8 in every BASELINE config)
+constexpr int kAttnSmem = 3 * kTileBytes + kHeads * kBiasStride * 4 + kMaxSrc * kS * sizeof(TapRec) + 64;
 
 // element (row, 16-byte unit) of a [64][512 B] tile, XOR-swizzled so ldmatrix is conflict free
 HMVIT_DEVINL uint32_t tile_off(int row, int unit) { return row * 512 + ((unit ^ (row & 7)) << 4); }
@@ -102,7 +105,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
   uint8_t* sK = smem + kTileBytes;
   uint8_t* sV = smem + 2 * kTileBytes;
   float* sBias = reinterpret_cast<float*>(smem + 3 * kTileBytes);          // [8][kBiasStride], log2 domain
-  TapRec* sTap = reinterpret_cast<TapRec*>(sBias + kHeads * kBiasStride);  // [64]
+  TapRec* sTapAll = reinterpret_cast<TapRec*>(sBias + kHeads * kBiasStride);  // [kMaxSrc][64]
+  int* sAnyVis = reinterpret_cast<int*>(sTapAll + kMaxSrc * kS);              // [kMaxSrc]
 
   // ---- stage Q (ego rows; softmax scale and log2(e) are folded into W_q) and the bias table ----
   {
@@ -135,23 +139,34 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
   //   ((2rb [+1]) - nt + 7) * 15 + (g - (2t + e) + 7)  =  bias_base - 15 nt - e  [+ 15]
   const int bias_base = (2 * rb + 7) * 15 + (g - 2 * t + 7);
 
-  for (int j = 0; j < nrec; ++j) {
-    if (p.cav_mask[b * p.L + j] == 0) continue;
-    ATTN_TS(j, 0);
-    // ---- taps + visibility for the 64 tokens of this group, source j -> ego i ----
-    int vis = 0;
-    if (threadIdx.x < kS) {
+  for (int j0 = 0; j0 < nrec; j0 += kMaxSrc) {
+  const int nsrc = min(kMaxSrc, nrec - j0);
+  // ---- taps + visibility of every (source, token) of this group, all sources in one parallel pass ----
+  __syncthreads();                               // previous pass (and the Q / bias staging) done with smem
+  if (threadIdx.x < kMaxSrc) sAnyVis[threadIdx.x] = 0;
+  __syncthreads();
+  for (int e = threadIdx.x; e < nsrc * kS; e += kAttnThreads) {
+    const int js = e >> 6, tk = e & 63, j = j0 + js;
+    TapRec rec; rec.x0 = 0; rec.y0 = 0; rec.vis = 0; rec.w01 = 0; rec.w23 = 0;
+    if (p.cav_mask[b * p.L + j] != 0) {
       const WarpMap wm = make_warp_map(p.T + ((static_cast<size_t>(b) * p.L + j) * p.L + i) * 16, p.H, p.W, p.cell);
-      int r, c; group_token(p.kind, gy, gx, threadIdx.x, p.H, p.W, r, c);
+      int r, c; group_token(p.kind, gy, gx, tk, p.H, p.W, r, c);
       double sx, sy; warp_src(wm, c, r, sx, sy);
-      vis = warp_visible(sx, sy, p.H, p.W) ? 1 : 0;
+      int vis = warp_visible(sx, sy, p.H, p.W) ? 1 : 0;
       if (p.key_mask != nullptr && p.key_mask[static_cast<size_t>(b * p.L + j) * N + r * p.W + c] == 0) vis = 0;
       const Taps tp = make_taps(sx, sy, p.H, p.W);
-      TapRec rec; rec.x0 = tp.x0; rec.y0 = tp.y0; rec.w00 = tp.w00; rec.w01 = tp.w01; rec.w10 = tp.w10; rec.w11 = tp.w11;
-      rec.vis = vis; rec.pad = 0;
-      sTap[threadIdx.x] = rec;
+      rec.x0 = static_cast<short>(tp.x0); rec.y0 = static_cast<short>(tp.y0); rec.vis = vis;
+      rec.w01 = pack_bf16x2(tp.w00, tp.w01); rec.w23 = pack_bf16x2(tp.w10, tp.w11);
+      if (vis) atomicOr(&sAnyVis[js], 1);
     }
-    if (!__syncthreads_or(vis)) continue;      // source invisible in this group: its softmax weight is exactly 0
+    sTapAll[e] = rec;
+  }
+  __syncthreads();
+
+  for (int js = 0; js < nsrc; ++js) {
+    const int j = j0 + js;
+    if (sAnyVis[js] == 0) continue;              // source invisible in this group: its softmax weight is exactly 0
+    const TapRec* sTap = sTapAll + js * kS;
     ATTN_TS(j, 1);
 
     // ---- gather projected K / V rows of source j: 4-tap blend with packed bf16 FMAs, + folded bias ----
@@ -173,13 +188,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
         const TapRec rec = sTap[s];
         uint4 ko = make_uint4(0, 0, 0, 0), vo = make_uint4(0, 0, 0, 0);
         if (rec.vis) {
-          const float w4[4] = {rec.w00, rec.w01, rec.w10, rec.w11};
+          // bf16 weights; a tap that falls outside the map has weight 0 and is not loaded
+          const uint32_t wq[4] = {rec.w01 & 0xffffu, rec.w01 >> 16, rec.w23 & 0xffffu, rec.w23 >> 16};
           uint4 kk[4], vv[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int yy = rec.y0 + (q >> 1), xx = rec.x0 + (q & 1);
             kk[q] = make_uint4(0, 0, 0, 0); vv[q] = make_uint4(0, 0, 0, 0);
-            if (w4[q] != 0.f) {
+            if (wq[q] != 0u) {
               const size_t off = static_cast<size_t>(yy * p.W + xx) * 32;
               kk[q] = __ldg(ksrc + off); vv[q] = __ldg(vsrc + off);
             }
@@ -188,7 +204,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
           vo = make_uint4(bv2[0], bv2[1], bv2[2], bv2[3]);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t w2 = pack_bf16x2(w4[q], w4[q]);
+            const uint32_t w2 = wq[q] | (wq[q] << 16);
             ko.x = hfma2_bf16(w2, kk[q].x, ko.x); ko.y = hfma2_bf16(w2, kk[q].y, ko.y);
             ko.z = hfma2_bf16(w2, kk[q].z, ko.z); ko.w = hfma2_bf16(w2, kk[q].w, ko.w);
             vo.x = hfma2_bf16(w2, vv[q].x, vo.x); vo.y = hfma2_bf16(w2, vv[q].y, vo.y);
@@ -262,19 +278,20 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
       const float mu0 = (mn0 == -INFINITY) ? 0.f : mn0, mu1 = (mn1 == -INFINITY) ? 0.f : mn1;
       const float al0 = ex2(mrow[hh][0] - mu0), al1 = ex2(mrow[hh][1] - mu1);
       mrow[hh][0] = mn0; mrow[hh][1] = mn1;
-      float rs0 = 0.f, rs1 = 0.f;
       uint32_t pa[4][4];                                         // P as A fragments: 4 x k16 over the 64 keys
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const float p0 = ex2(sacc[nt][0] - mu0), p1 = ex2(sacc[nt][1] - mu0);
         const float p2 = ex2(sacc[nt][2] - mu1), p3 = ex2(sacc[nt][3] - mu1);
-        rs0 += p0 + p1; rs1 += p2 + p3;
         pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
         pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
       }
-      rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
-      rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
-      lrow[hh][0] = lrow[hh][0] * al0 + rs0; lrow[hh][1] = lrow[hh][1] * al1 + rs1;
+      // running denominator: l = l * alpha + rowsum(P), the row sums come from the tensor core too
+      // (P x ones), i.e. from exactly the bf16 probabilities that multiply V
+      float lacc[4] = {lrow[hh][0] * al0, 0.f, lrow[hh][1] * al1, 0.f};
+#pragma unroll
+      for (int kc = 0; kc < 4; ++kc) mma_bf16(lacc, pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], 0x3F803F80u, 0x3F803F80u);
+      lrow[hh][0] = lacc[0]; lrow[hh][1] = lacc[2];
 #pragma unroll
       for (int n = 0; n < 4; ++n) { o[hh][n][0] *= al0; o[hh][n][1] *= al0; o[hh][n][2] *= al1; o[hh][n][3] *= al1; }
       // O_h += P V_h
@@ -291,8 +308,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
         }
       }
     }
-    __syncthreads();     // compute phase done before sTap / sK / sV are rewritten for the next source
+    __syncthreads();     // compute phase done before sK / sV are rewritten for the next source
     ATTN_TS(j, 3);
+  }
   }
 
   // ---- normalise, stage in smem (reuse sK), coalesced store ----
