@@ -216,7 +216,7 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
   p.q = static_cast<const __nv_bfloat16*>(a->q); p.k = static_cast<const __nv_bfloat16*>(a->k);
   p.v = static_cast<const __nv_bfloat16*>(a->v); p.bk = a->bk; p.bv = a->bv; p.bias_table = a->bias_table; p.key_mask = a->key_mask;
   p.out = static_cast<__nv_bfloat16*>(a->out);
-  dim3 grid((a->H / 8) * (a->W / 8), a->B * a->L);
+  dim3 grid((a->H / 8) * (a->W / 8) * 2, a->B * a->L);      // x: (token group, head group)
   group_attn_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;

@@ -9,7 +9,7 @@
 //      projection) with 16-byte vector loads, blends the 4 taps on top of the folded
 //      bias with packed bf16 FMAs and stores them swizzled in shared memory;
 //   3. runs S = Q K^T (+ relative position bias, key mask), an online softmax over all sources and
-//      O += P V on the tensor cores, fp32 accumulation, one warp per 16 query rows x 4 heads (8 warps).
+//      O += P V on the tensor cores, fp32 accumulation, one warp per 16 query rows x 4 heads.
 // Sources with no visible key in this group are skipped entirely (their softmax weight is exactly 0).
 // window / grid partition differ only in the token table (hetero_fusion.py:384-389 vs 427-431).
 //
@@ -46,17 +46,19 @@ struct AttnParams {
   __nv_bfloat16* out;          // [B*L*N][256]
 };
 
-constexpr int kAttnThreads = 256;
-constexpr int kTileBytes = kS * kC * 2;          // 32 KB: 64 tokens x 256 ch bf16
-constexpr int kBiasStride = 232;                 // [8 heads][225 (+7 pad)]
-// per (source, token) gather record, 16 bytes: corner (x0, y0), visibility, 4 tap weights already
-// duplicated into bf16x2 pairs (the blend runs on packed bf16 FMAs)
-struct TapRec { short x0, y0; int vis; uint32_t w01; uint32_t w23; };   // w01 = (w00, w01) bf16 pair, w23 = (w10, w11)
-constexpr int kMaxSrc = 8;                       // sources handled per tap pass (L <= 8 in every BASELINE config)
-constexpr int kAttnSmem = 3 * kTileBytes + kHeads * kBiasStride * 4 + kMaxSrc * kS * sizeof(TapRec) + 64;
+constexpr int kAttnThreads = 128;
+constexpr int kHG = 4;                           // heads per CTA (a CTA owns one head group = 128 channels of one group of tokens)
+constexpr int kRowBytes = kHG * kDh * 2;         // 256 B: one token row of the head group
+constexpr int kTileBytes = kS * kRowBytes;       // 16 KB: 64 tokens x 128 ch bf16
+constexpr int kBiasStride = 232;                 // [4 heads][225 (+7 pad)]
+// per (source, token) gather record, 12 bytes: corner (x0, y0) and the 4 tap weights as bf16.  A token is
+// visible iff some weight is non-zero (the nearest in-range corner always has weight >= 1/4).
+struct TapRec { short x0, y0; uint32_t w01; uint32_t w23; };     // w01 = (w00, w01), w23 = (w10, w11)
+constexpr int kMaxSrc = 5;                       // sources per tap pass
+constexpr int kAttnSmem = 3 * kTileBytes + kHG * kBiasStride * 4 + kMaxSrc * kS * sizeof(TapRec) + 32;
 
-// element (row, 16-byte unit) of a [64][512 B] tile, XOR-swizzled so ldmatrix is conflict free
-HMVIT_DEVINL uint32_t tile_off(int row, int unit) { return row * 512 + ((unit ^ (row & 7)) << 4); }
+// element (row, 16-byte unit 0..15) of a [64][256 B] tile, XOR-swizzled so ldmatrix is conflict free
+HMVIT_DEVINL uint32_t tile_off(int row, int unit) { return row * kRowBytes + ((unit ^ (row & 7)) << 4); }
 
 HMVIT_DEVINL void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -85,49 +87,53 @@ HMVIT_DEVINL void group_token(int kind, int gy, int gx, int s, int H, int W, int
   else           { r = s1 * (H / kWin) + gy; c = s2 * (W / kWin) + gx; }
 }
 
-// 8 warps: warp = (head group hg = warp / 4, query row block rb = warp % 4); each warp owns 16 query
-// rows x 4 heads.  All 8 warps share the gather of every source's K / V tile.
-__global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnParams p) {
+// One CTA = (scene b, ego i, group of 64 tokens, head group of 4 heads); 4 warps, warp w owns query rows
+// [16w, 16w+16) x 4 heads.  Four CTAs are resident per SM (55 KB of shared memory, 128 registers), so
+// gather phases (L2 latency) of some overlap the tensor-core / softmax phases of the others.
+__global__ void __launch_bounds__(kAttnThreads, 4) group_attn_kernel(const AttnParams p) {
   const int a = blockIdx.y;
   const int b = a / p.L, i = a - b * p.L;
   const int nrec = p.record_len[b];
   if (i >= nrec || (p.ego_only && i != 0)) return;
   const int N = p.H * p.W;
   const int GX = p.W / kWin;
-  const int gy = blockIdx.x / GX, gx = blockIdx.x - gy * GX;
+  const int grp = blockIdx.x >> 1, hgc = blockIdx.x & 1;      // token group, head group
+  const int gy = grp / GX, gx = grp - gy * GX;
   const int te = p.mode[a] != 0 ? 1 : 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rb = warp & 3, hg = warp >> 2;
+  const int rb = warp;
   const int g = lane >> 2, t = lane & 3;
+  const int hl = lane >> 4, u16 = lane & 15;                  // half-warp (one token each) and 16-byte unit within the 256-byte row
 
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTileBytes;
   uint8_t* sV = smem + 2 * kTileBytes;
-  float* sBias = reinterpret_cast<float*>(smem + 3 * kTileBytes);          // [8][kBiasStride], log2 domain
-  TapRec* sTapAll = reinterpret_cast<TapRec*>(sBias + kHeads * kBiasStride);  // [kMaxSrc][64]
+  float* sBias = reinterpret_cast<float*>(smem + 3 * kTileBytes);             // [4][kBiasStride], log2 domain
+  TapRec* sTapAll = reinterpret_cast<TapRec*>(sBias + kHG * kBiasStride);     // [kMaxSrc][64]
   int* sAnyVis = reinterpret_cast<int*>(sTapAll + kMaxSrc * kS);              // [kMaxSrc]
 
+  const int cu0 = hgc * 16;                                    // first 16-byte unit of this head group in a 512-byte row
   // ---- stage Q (ego rows; softmax scale and log2(e) are folded into W_q) and the bias table ----
   {
-    const uint4* qsrc = reinterpret_cast<const uint4*>(p.q) + static_cast<size_t>(a) * N * 32;
+    const uint4* qsrc = reinterpret_cast<const uint4*>(p.q) + static_cast<size_t>(a) * N * 32 + cu0 + u16;
 #pragma unroll 4
     for (int tt = 0; tt < 8; ++tt) {
-      const int s = warp * 8 + tt;
+      const int s = warp * 16 + tt * 2 + hl;
       int r, c; group_token(p.kind, gy, gx, s, p.H, p.W, r, c);
-      const uint4 v = __ldg(qsrc + static_cast<size_t>(r * p.W + c) * 32 + lane);
-      *reinterpret_cast<uint4*>(sQ + tile_off(s, lane)) = v;
+      const uint4 v = __ldg(qsrc + static_cast<size_t>(r * p.W + c) * 32);
+      *reinterpret_cast<uint4*>(sQ + tile_off(s, u16)) = v;
     }
-    for (int e = threadIdx.x; e < 225 * kHeads; e += kAttnThreads) {
-      const int idx = e >> 3, h = e & 7;
-      sBias[h * kBiasStride + idx] = __ldg(p.bias_table + e) * 1.4426950408889634f;
+    for (int e = threadIdx.x; e < 225 * kHG; e += kAttnThreads) {
+      const int idx = e >> 2, h = e & 3;
+      sBias[h * kBiasStride + idx] = __ldg(p.bias_table + idx * kHeads + hgc * kHG + h) * 1.4426950408889634f;
     }
   }
 
-  float o[4][4][4];
-  float mrow[4][2], lrow[4][2];
+  float o[kHG][4][4];
+  float mrow[kHG][2], lrow[kHG][2];
 #pragma unroll
-  for (int h = 0; h < 4; ++h) {
+  for (int h = 0; h < kHG; ++h) {
     mrow[h][0] = mrow[h][1] = -INFINITY; lrow[h][0] = lrow[h][1] = 0.f;
 #pragma unroll
     for (int n = 0; n < 4; ++n) { o[h][n][0] = o[h][n][1] = o[h][n][2] = o[h][n][3] = 0.f; }
@@ -147,17 +153,19 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
   __syncthreads();
   for (int e = threadIdx.x; e < nsrc * kS; e += kAttnThreads) {
     const int js = e >> 6, tk = e & 63, j = j0 + js;
-    TapRec rec; rec.x0 = 0; rec.y0 = 0; rec.vis = 0; rec.w01 = 0; rec.w23 = 0;
+    TapRec rec; rec.x0 = 0; rec.y0 = 0; rec.w01 = 0; rec.w23 = 0;
     if (p.cav_mask[b * p.L + j] != 0) {
       const WarpMap wm = make_warp_map(p.T + ((static_cast<size_t>(b) * p.L + j) * p.L + i) * 16, p.H, p.W, p.cell);
       int r, c; group_token(p.kind, gy, gx, tk, p.H, p.W, r, c);
       double sx, sy; warp_src(wm, c, r, sx, sy);
-      int vis = warp_visible(sx, sy, p.H, p.W) ? 1 : 0;
-      if (p.key_mask != nullptr && p.key_mask[static_cast<size_t>(b * p.L + j) * N + r * p.W + c] == 0) vis = 0;
-      const Taps tp = make_taps(sx, sy, p.H, p.W);
-      rec.x0 = static_cast<short>(tp.x0); rec.y0 = static_cast<short>(tp.y0); rec.vis = vis;
-      rec.w01 = pack_bf16x2(tp.w00, tp.w01); rec.w23 = pack_bf16x2(tp.w10, tp.w11);
-      if (vis) atomicOr(&sAnyVis[js], 1);
+      bool vis = warp_visible(sx, sy, p.H, p.W);
+      if (p.key_mask != nullptr && p.key_mask[static_cast<size_t>(b * p.L + j) * N + r * p.W + c] == 0) vis = false;
+      if (vis) {
+        const Taps tp = make_taps(sx, sy, p.H, p.W);
+        rec.x0 = static_cast<short>(tp.x0); rec.y0 = static_cast<short>(tp.y0);
+        rec.w01 = pack_bf16x2(tp.w00, tp.w01); rec.w23 = pack_bf16x2(tp.w10, tp.w11);
+        atomicOr(&sAnyVis[js], 1);
+      }
     }
     sTapAll[e] = rec;
   }
@@ -169,25 +177,26 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
     const TapRec* sTap = sTapAll + js * kS;
     ATTN_TS(j, 1);
 
-    // ---- gather projected K / V rows of source j: 4-tap blend with packed bf16 FMAs, + folded bias ----
+    // ---- gather projected K / V rows of source j (this head group's 256 bytes): 4-tap blend with packed
+    //      bf16 FMAs on top of the folded bias; a half-warp per token ----
     {
       const int tj = p.mode[b * p.L + j] != 0 ? 1 : 0;
-      const uint4* ksrc = reinterpret_cast<const uint4*>(p.k) + te * plane + static_cast<size_t>(b * p.L + j) * N * 32 + lane;
-      const uint4* vsrc = reinterpret_cast<const uint4*>(p.v) + te * plane + static_cast<size_t>(b * p.L + j) * N * 32 + lane;
+      const uint4* ksrc = reinterpret_cast<const uint4*>(p.k) + te * plane + static_cast<size_t>(b * p.L + j) * N * 32 + cu0 + u16;
+      const uint4* vsrc = reinterpret_cast<const uint4*>(p.v) + te * plane + static_cast<size_t>(b * p.L + j) * N * 32 + cu0 + u16;
       uint32_t bk2[4], bv2[4];
       {
-        const float4* pk = reinterpret_cast<const float4*>(p.bk + (te * 2 + tj) * kC + lane * 8);
-        const float4* pv = reinterpret_cast<const float4*>(p.bv + (te * 2 + tj) * kC + lane * 8);
+        const float4* pk = reinterpret_cast<const float4*>(p.bk + (te * 2 + tj) * kC + (cu0 + u16) * 8);
+        const float4* pv = reinterpret_cast<const float4*>(p.bv + (te * 2 + tj) * kC + (cu0 + u16) * 8);
         const float4 k0 = __ldg(pk), k1 = __ldg(pk + 1), v0 = __ldg(pv), v1 = __ldg(pv + 1);
         bk2[0] = pack_bf16x2(k0.x, k0.y); bk2[1] = pack_bf16x2(k0.z, k0.w); bk2[2] = pack_bf16x2(k1.x, k1.y); bk2[3] = pack_bf16x2(k1.z, k1.w);
         bv2[0] = pack_bf16x2(v0.x, v0.y); bv2[1] = pack_bf16x2(v0.z, v0.w); bv2[2] = pack_bf16x2(v1.x, v1.y); bv2[3] = pack_bf16x2(v1.z, v1.w);
       }
 #pragma unroll 2
       for (int tt = 0; tt < 8; ++tt) {
-        const int s = warp * 8 + tt;
+        const int s = warp * 16 + tt * 2 + hl;
         const TapRec rec = sTap[s];
         uint4 ko = make_uint4(0, 0, 0, 0), vo = make_uint4(0, 0, 0, 0);
-        if (rec.vis) {
+        if ((rec.w01 | rec.w23) != 0u) {
           // bf16 weights; a tap that falls outside the map has weight 0 and is not loaded
           const uint32_t wq[4] = {rec.w01 & 0xffffu, rec.w01 >> 16, rec.w23 & 0xffffu, rec.w23 >> 16};
           uint4 kk[4], vv[4];
@@ -211,8 +220,8 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
             vo.z = hfma2_bf16(w2, vv[q].z, vo.z); vo.w = hfma2_bf16(w2, vv[q].w, vo.w);
           }
         }
-        *reinterpret_cast<uint4*>(sK + tile_off(s, lane)) = ko;
-        *reinterpret_cast<uint4*>(sV + tile_off(s, lane)) = vo;
+        *reinterpret_cast<uint4*>(sK + tile_off(s, u16)) = ko;
+        *reinterpret_cast<uint4*>(sV + tile_off(s, u16)) = vo;
       }
     }
     __syncthreads();
@@ -222,16 +231,16 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
     uint32_t vbits = 0;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      vbits |= (sTap[nt * 8 + 2 * t].vis ? 1u : 0u) << (nt * 2);
-      vbits |= (sTap[nt * 8 + 2 * t + 1].vis ? 1u : 0u) << (nt * 2 + 1);
+      const TapRec r0 = sTap[nt * 8 + 2 * t], r1 = sTap[nt * 8 + 2 * t + 1];
+      vbits |= ((r0.w01 | r0.w23) != 0u ? 1u : 0u) << (nt * 2);
+      vbits |= ((r1.w01 | r1.w23) != 0u ? 1u : 0u) << (nt * 2 + 1);
     }
 
     // ---- tensor-core phase: this warp's 16 query rows x 4 heads ----
 #pragma unroll
-    for (int hh = 0; hh < 4; ++hh) {
-      const int h = hg * 4 + hh;
+    for (int hh = 0; hh < kHG; ++hh) {
       // accumulators start from the relative position bias (log2 domain)
-      const float* bh = sBias + h * kBiasStride + bias_base;
+      const float* bh = sBias + hh * kBiasStride + bias_base;
       float sacc[8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
@@ -243,14 +252,14 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
         uint32_t a0, a1, a2, a3;
         {
           const int row = rb * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-          const int unit = h * 4 + kk2 * 2 + (lane >> 4);
+          const int unit = hh * 4 + kk2 * 2 + (lane >> 4);
           ldsm_x4(sQ_u + tile_off(row, unit), a0, a1, a2, a3);
         }
 #pragma unroll
         for (int np = 0; np < 4; ++np) {                        // pairs of key n-tiles
           uint32_t b0, b1, b2, b3;
           const int row = np * 16 + (lane & 7) + (lane >> 4) * 8;
-          const int unit = h * 4 + kk2 * 2 + ((lane >> 3) & 1);
+          const int unit = hh * 4 + kk2 * 2 + ((lane >> 3) & 1);
           ldsm_x4(sK_u + tile_off(row, unit), b0, b1, b2, b3);
           mma_bf16(sacc[np * 2], a0, a1, a2, a3, b0, b1);
           mma_bf16(sacc[np * 2 + 1], a0, a1, a2, a3, b2, b3);
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
         for (int np = 0; np < 2; ++np) {                        // pairs of dim n-tiles
           uint32_t b0, b1, b2, b3;
           const int row = kc * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-          const int unit = h * 4 + np * 2 + (lane >> 4);
+          const int unit = hh * 4 + np * 2 + (lane >> 4);
           ldsm_x4_t(sV_u + tile_off(row, unit), b0, b1, b2, b3);
           mma_bf16(o[hh][np * 2], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], b0, b1);
           mma_bf16(o[hh][np * 2 + 1], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], b2, b3);
@@ -316,13 +325,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
   // ---- normalise, stage in smem (reuse sK), coalesced store ----
   __syncthreads();
 #pragma unroll
-  for (int hh = 0; hh < 4; ++hh) {
-    const int h = hg * 4 + hh;
+  for (int hh = 0; hh < kHG; ++hh) {
     const float il0 = lrow[hh][0] > 0.f ? 1.0f / lrow[hh][0] : 0.f;
     const float il1 = lrow[hh][1] > 0.f ? 1.0f / lrow[hh][1] : 0.f;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
-      const int col = h * kDh + n * 8 + 2 * t;                   // channel
+      const int col = hh * kDh + n * 8 + 2 * t;                  // channel within the head group
       const int r0 = rb * 16 + g, r1 = r0 + 8;
       *reinterpret_cast<uint32_t*>(sK + tile_off(r0, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[hh][n][0] * il0, o[hh][n][1] * il0);
       *reinterpret_cast<uint32_t*>(sK + tile_off(r1, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[hh][n][2] * il1, o[hh][n][3] * il1);
@@ -330,12 +338,12 @@ __global__ void __launch_bounds__(kAttnThreads, 2) group_attn_kernel(const AttnP
   }
   __syncthreads();
   {
-    uint4* dst = reinterpret_cast<uint4*>(p.out) + static_cast<size_t>(a) * N * 32;
+    uint4* dst = reinterpret_cast<uint4*>(p.out) + static_cast<size_t>(a) * N * 32 + cu0 + u16;
 #pragma unroll 4
     for (int tt = 0; tt < 8; ++tt) {
-      const int s = warp * 8 + tt;
+      const int s = warp * 16 + tt * 2 + hl;
       int r, c; group_token(p.kind, gy, gx, s, p.H, p.W, r, c);
-      dst[static_cast<size_t>(r * p.W + c) * 32 + lane] = *reinterpret_cast<const uint4*>(sK + tile_off(s, lane));
+      dst[static_cast<size_t>(r * p.W + c) * 32] = *reinterpret_cast<const uint4*>(sK + tile_off(s, u16));
     }
   }
 }
