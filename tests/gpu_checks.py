@@ -477,3 +477,48 @@ CHECKS = {
     "fusion_config5_scene": check_fusion_config5_scene,
     "errors": check_errors,
 }
+
+
+# ----------------------------------------------------------------------------------------------
+def check_cuda_graph():
+    """The whole forward only enqueues work on the caller's stream (no host sync, no allocation inside the
+    C-ABI): it can be captured into a CUDA graph and replayed; the replay is bit-identical."""
+    cfg, P, net = _mk_module(0)
+    x, T, md, rl, mask = _scene(2, 4, 32, 48, [4, 3], seed=9)
+    inp = [t.to(DEV) for t in (x, T, md, rl, mask)]
+    with torch.no_grad():
+        y_ref = net(*inp).clone()
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            net(*inp)                                  # warm-up on the capture stream (packs weights, sizes workspace)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                y_g = net(*inp)
+        torch.cuda.current_stream().wait_stream(s)
+        inp[0].mul_(0.5)                               # new input values in the captured buffer
+        y_new_ref = net(*inp).clone()
+        g.replay()
+        torch.cuda.synchronize()
+    res = {"replay_vs_eager_max_abs": float((y_g - y_new_ref).abs().max()), "changed": float((y_new_ref - y_ref).abs().max())}
+    assert res["replay_vs_eager_max_abs"] == 0.0 and res["changed"] > 0.0, res
+    return res
+
+
+def check_ragged_batch():
+    """Edge cases of the batch structure: single-agent scenes (record_len 1), fully populated scenes and
+    mixed record_len in one batch, all-camera and all-LiDAR scenes; against the oracle."""
+    cfg, P, net = _mk_module(1)
+    B, L, H, W = 4, 5, 16, 24
+    mode = [[1, 0, 0, 0, 0], [0, 0, 0, 0, 0], [1, 1, 1, 1, 1], [0, 1, 0, 1, 0]]
+    x, T, md, rl, mask = _scene(B, L, H, W, [1, 5, 3, 2], seed=21, mode=mode, tx=12, ty=6)
+    with torch.no_grad():
+        y = net(x.to(DEV), T.to(DEV), md.to(DEV), rl.to(DEV), mask.to(DEV)).cpu()
+    ref = O.hetero_fusion(x, T, md, rl, mask, P, cfg)
+    res = {"rel_l2_vs_oracle": rel_l2(y, ref), "per_scene": [round(rel_l2(y[b], ref[b]), 6) for b in range(B)]}
+    assert all(v < 1e-3 for v in res["per_scene"]), res
+    return res
+
+
+CHECKS.update({"cuda_graph": check_cuda_graph, "ragged_batch": check_ragged_batch})
