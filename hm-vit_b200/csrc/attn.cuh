@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kAttnThreads, 4) group_attn_kernel(const AttnP
   const int nsrc = min(kMaxSrc, nrec - j0);
   // ---- taps + visibility of every (source, token) of this group, all sources in one parallel pass ----
   __syncthreads();                               // previous pass (and the Q / bias staging) done with smem
+  ATTN_TS(j0, 0);
   if (threadIdx.x < kMaxSrc) sAnyVis[threadIdx.x] = 0;
   __syncthreads();
   for (int e = threadIdx.x; e < nsrc * kS; e += kAttnThreads) {

@@ -21,9 +21,9 @@ lib.hmvit_debug_attn_ts(buf)
 ts = np.array(buf[:], dtype=np.int64).reshape(8, 8, 4)
 for cta in range(8):
     base = ts[cta][ts[cta] > 0].min() if (ts[cta] > 0).any() else 0
-    out = []
+    out = [f"taps@{int(ts[cta,0,0]-base)}"]
     for j in range(5):
         e = ts[cta, j]
-        if e[0] == 0: continue
-        out.append(f"j{j}: taps+{int(e[1]-e[0])} gather+{int(e[2]-e[1])} compute+{int(e[3]-e[2])} (t0={int(e[0]-base)})")
+        if e[1] == 0: continue
+        out.append(f"j{j}: start@{int(e[1]-base)} gather+{int(e[2]-e[1])} compute+{int(e[3]-e[2])}")
     print("cta", cta, " | ".join(out))
