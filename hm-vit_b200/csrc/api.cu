@@ -3,13 +3,16 @@
 #include "../../include/hmvit_b200.h"
 #include "rowgemm.cuh"
 #include "attn.cuh"
+#include "attn_tc.cuh"
 #include "chain.cuh"
 #include "qkv.cuh"
+#include "probe.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -202,12 +205,17 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a->cell > 0.0, "group_attn: cell size must be positive");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
+  // Two implementations of the same contract: the mma.sync kernel (attn.cuh, 4 CTAs / SM, every warp gathers and
+  // computes) is the default -- it is the faster one today (0.74 vs 1.0 ms per launch at config 2); the
+  // warp-specialised tcgen05 / TMEM kernel (attn_tc.cuh) is selected with HMVIT_ATTN_IMPL=tc and is kept
+  // parity-tested (profiles/r1_attention_study.md explains what bounds it).
+  static bool legacy = true;
   std::call_once(once, [] {
+    const char* impl = getenv("HMVIT_ATTN_IMPL");
+    legacy = !(impl != nullptr && strcmp(impl, "tc") == 0);
     attr_err = cudaFuncSetAttribute(group_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-#ifdef HMVIT_ATTN_CARVEOUT
     if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(group_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, HMVIT_ATTN_CARVEOUT);
-#endif
+      attr_err = cudaFuncSetAttribute(group_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg::SMEM_BYTES);
   });
   HMVIT_CHECK_CUDA(attr_err);
   AttnParams p;
@@ -217,7 +225,8 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
   p.v = static_cast<const __nv_bfloat16*>(a->v); p.bk = a->bk; p.bv = a->bv; p.bias_table = a->bias_table; p.key_mask = a->key_mask;
   p.out = static_cast<__nv_bfloat16*>(a->out);
   dim3 grid((a->H / 8) * (a->W / 8) * 2, a->B * a->L);      // x: (token group, head group)
-  group_attn_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  if (legacy) group_attn_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  else group_attn_tc_kernel<<<grid, AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }
@@ -306,7 +315,43 @@ extern "C" size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, 
 
 extern "C" int hmvit_fusion_launch_count(int32_t num_iters, int32_t head) { return num_iters * 2 * 3 + (head ? 2 : 0); }
 
+static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream);
+
+// Scenes are independent, so the forward can be issued scene chunk by scene chunk through all stages with
+// the same workspace (HMVIT_SCENE_CHUNK=n).  Measured on B200 at config 2: slower than one launch per stage
+// over the whole batch (wave quantisation of the persistent GEMM kernels outweighs the L2 residency), so
+// the default is the whole batch.
+static int scene_chunk() {
+  static int chunk = [] {
+    const char* e = getenv("HMVIT_SCENE_CHUNK");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : (1 << 30);
+  }();
+  return chunk;
+}
+
 extern "C" int hmvit_fusion_forward(const HmvitFusionArgs* a, void* stream) {
+  HMVIT_CHECK_ARG(a != nullptr, "fusion_forward: null args");
+  HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->H > 0 && a->W > 0, "fusion_forward: bad shape");
+  const int chunk = scene_chunk();
+  const size_t per_scene = static_cast<size_t>(a->L) * 256 * a->H * a->W;
+  for (int b0 = 0; b0 < a->B; b0 += chunk) {
+    HmvitFusionArgs c = *a;
+    c.B = (a->B - b0 < chunk) ? (a->B - b0) : chunk;
+    c.x = a->x + b0 * per_scene;
+    c.T = a->T + static_cast<size_t>(b0) * a->L * a->L * 16;
+    c.mode = a->mode + b0 * a->L;
+    c.record_len = a->record_len + b0;
+    c.cav_mask = a->cav_mask + b0 * a->L;
+    c.xres = a->xres ? a->xres + b0 * per_scene : nullptr;
+    c.out = a->out ? a->out + static_cast<size_t>(b0) * 256 * a->H * a->W : nullptr;
+    int rc = fusion_forward_chunk(&c, stream);
+    if (rc) return rc;
+  }
+  return HMVIT_OK;
+}
+
+static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a != nullptr, "fusion_forward: null args");
   HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->H > 0 && a->W > 0, "fusion_forward: bad shape");
   HMVIT_CHECK_ARG(a->H % 8 == 0 && a->W % 8 == 0, "fusion_forward: H and W must be divisible by the window size 8");
@@ -406,9 +451,25 @@ extern "C" int hmvit_debug_probe(uint32_t* out2, void* stream) {
   return HMVIT_OK;
 }
 
+extern "C" int hmvit_debug_umma(const void* A, const void* Bm, float* D, int N, int b_mn_major, unsigned lbo, unsigned sbo,
+                                unsigned kstep_bytes, void* stream) {
+  HMVIT_CHECK_ARG(A && Bm && D, "debug_umma: null pointer");
+  HMVIT_CHECK_ARG(N >= 16 && N <= 128 && N % 16 == 0, "debug_umma: N must be 16..128, multiple of 16");
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960); });
+  umma_probe_kernel<<<1, 128, 16384 + 16384 + 1024, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(Bm), D, N, b_mn_major, lbo, sbo, kstep_bytes);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
 #ifdef HMVIT_TS
 extern "C" int hmvit_debug_attn_ts(unsigned long long* host_out /* [8][8][4] */) {
   HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_attn_ts, sizeof(unsigned long long) * 8 * 8 * 4));
+  return HMVIT_OK;
+}
+extern "C" int hmvit_debug_tc_ts(unsigned long long* host_out /* [8][3][64] */) {
+  HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_tc_ts, sizeof(unsigned long long) * 8 * 3 * 64));
   return HMVIT_OK;
 }
 extern "C" int hmvit_debug_chain_ts(unsigned long long* host_out /* [2][16][16] */) {

@@ -11,3 +11,24 @@ pytestmark = pytest.mark.gpu
 def test_gpu_check(name):
     res = gpu_checks.CHECKS[name]()
     print(name, res)
+
+
+TC_CHECKS = ["attention_golden", "fusion_golden", "fusion_config2_scene", "ragged_batch", "fusion_properties"]
+
+
+@pytest.mark.parametrize("name", TC_CHECKS)
+def test_gpu_check_tcgen05_attention(name):
+    """The same parity checks with the warp-specialised tcgen05 / TMEM attention kernel (attn_tc.cuh) selected
+    instead of the default mma.sync one.  The switch is read once per process, hence the subprocess."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HMVIT_ATTN_IMPL="tc")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bringup.py"), "--one", name], capture_output=True,
+                       text=True, env=env, timeout=600)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert line, r.stdout[-500:] + r.stderr[-500:]
+    res = json.loads(line[-1])
+    assert res["status"] == "ok", res
