@@ -10,11 +10,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("HMVIT_LIB", os.path.join(_HERE, "libhmvit_b200.so"))   # HMVIT_LIB: tuning builds only
 
 GEMM_QKV, GEMM_OUT, GEMM_FFN1, GEMM_FFN2, GEMM_HEAD1, GEMM_HEAD2, GEMM_QKV_NOLN = range(7)
+GEMM_LN_LIN_CM, GEMM_LIN_CM, GEMM_LIN_ROWS, GEMM_ROWS_LIN_CM = range(7, 11)
 
 EXPORTS = (
     "hmvit_abi_version", "hmvit_last_error", "hmvit_rowgemm", "hmvit_group_attn", "hmvit_warp_bilinear",
     "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
     "hmvit_debug_probe", "hmvit_out_ffn_chain",
+    "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
+    "hmvit_bwd_wgrad", "hmvit_group_attn_bwd",
 )
 
 
@@ -40,7 +43,25 @@ class AttnArgs(C.Structure):
                 ("mode", C.c_void_p), ("record_len", C.c_void_p), ("cav_mask", C.c_void_p), ("T", C.c_void_p),
                 ("cell", C.c_double), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
                 ("bk", C.c_void_p), ("bv", C.c_void_p), ("bias_table", C.c_void_p), ("key_mask", C.c_void_p),
-                ("out", C.c_void_p)]
+                ("out", C.c_void_p), ("lse", C.c_void_p)]
+
+
+class WgradArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("N", C.c_int32), ("mode", C.c_void_p), ("record_len", C.c_void_p),
+                ("ego_only", C.c_int32), ("a", C.c_void_p), ("a_rows_bf16", C.c_int32), ("b", C.c_void_p),
+                ("b_rows_bf16", C.c_int32), ("b_stats", C.c_void_p), ("dw", C.c_void_p),
+                ("dw_rows", C.c_int32), ("dw_row0", C.c_int32)]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("kind", C.c_int32), ("ego_only", C.c_int32),
+                ("mode", C.c_void_p), ("record_len", C.c_void_p), ("cav_mask", C.c_void_p), ("T", C.c_void_p),
+                ("cell", C.c_double), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+                ("bk", C.c_void_p), ("bv", C.c_void_p), ("bias_table", C.c_void_p),
+                ("o", C.c_void_p), ("d_o", C.c_void_p), ("lse", C.c_void_p),
+                ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+                ("dbk", C.c_void_p), ("dbv", C.c_void_p), ("dbias_table", C.c_void_p)]
 
 
 class StageWeights(C.Structure):
@@ -96,7 +117,18 @@ def load():
     lib.hmvit_fusion_launch_count.restype = C.c_int
     lib.hmvit_debug_probe.argtypes = [C.c_void_p, C.c_void_p]
     lib.hmvit_debug_probe.restype = C.c_int
-    if lib.hmvit_abi_version() != 1:
+    i32, vp = C.c_int32, C.c_void_p
+    lib.hmvit_bwd_row_stats.argtypes = [vp, vp, i32, i32, i32, vp, i32, C.c_float, vp]
+    lib.hmvit_bwd_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp]
+    lib.hmvit_bwd_gelu.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.hmvit_bwd_cast_bf16.argtypes = [vp, vp, C.c_size_t, vp]
+    lib.hmvit_bwd_colsum.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp]
+    lib.hmvit_bwd_wgrad.argtypes = [C.POINTER(WgradArgs), vp]
+    lib.hmvit_group_attn_bwd.argtypes = [C.POINTER(AttnBwdArgs), vp]
+    for fn in ("hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
+               "hmvit_bwd_wgrad", "hmvit_group_attn_bwd"):
+        getattr(lib, fn).restype = C.c_int
+    if lib.hmvit_abi_version() != 2:
         raise ImportError("libhmvit_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -4,6 +4,8 @@
 #include "rowgemm.cuh"
 #include "attn.cuh"
 #include "attn_tc.cuh"
+#include "attn_bwd.cuh"
+#include "bwd.cuh"
 #include "chain.cuh"
 #include "qkv.cuh"
 #include "probe.cuh"
@@ -15,6 +17,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <string>
+#include <type_traits>
 
 using namespace hmvit;
 
@@ -107,8 +110,9 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
   HMVIT_CHECK_ARG(a->B * a->L <= 65535, "rowgemm: B*L exceeds grid limit");
   HMVIT_CHECK_ARG(a->n_out > 0 && a->n_out % 128 == 0 && a->n_out <= 32 * 128, "rowgemm: n_out must be a multiple of 128");
   HMVIT_CHECK_ARG(a->mode && a->record_len && a->a && a->w[0] && a->w[1] && a->bias && a->out, "rowgemm: null pointer");
-  const bool tf32 = variant >= HMVIT_GEMM_FFN1 && variant <= HMVIT_GEMM_HEAD2;
-  HMVIT_CHECK_ARG(variant >= HMVIT_GEMM_QKV && variant <= HMVIT_GEMM_QKV_NOLN, "rowgemm: unknown variant");
+  const bool tf32 = (variant >= HMVIT_GEMM_FFN1 && variant <= HMVIT_GEMM_HEAD2) ||
+                    (variant >= HMVIT_GEMM_LN_LIN_CM && variant <= HMVIT_GEMM_LIN_ROWS);
+  HMVIT_CHECK_ARG(variant >= HMVIT_GEMM_QKV && variant <= HMVIT_GEMM_ROWS_LIN_CM, "rowgemm: unknown variant");
   if (variant == HMVIT_GEMM_QKV || variant == HMVIT_GEMM_QKV_NOLN) HMVIT_CHECK_ARG(a->n_out == 1280, "rowgemm: QKV expects n_out == 1280");
   else HMVIT_CHECK_ARG(a->n_out == 256, "rowgemm: n_out must be 256 for this variant");
   HMVIT_CHECK_ARG((a->ln_gamma == nullptr) == (a->ln_beta == nullptr), "rowgemm: ln_gamma and ln_beta must both be set or both be null");
@@ -154,6 +158,23 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
       p.a_cm = static_cast<const float*>(a->a); p.out_cm = static_cast<float*>(a->out);
       p.tile_ego_only = 1; p.out_L = 1;
       return launch_rowgemm<4, PRO_CM_CAST, EPI_CM_STORE>(m0, m1, p, st);
+    case HMVIT_GEMM_LN_LIN_CM:
+      p.a_cm = static_cast<const float*>(a->a); p.out_cm = static_cast<float*>(a->out);
+      p.tile_ego_only = a->ego_only ? 1 : 0;
+      return launch_rowgemm<4, PRO_CM_LN, EPI_CM_STORE>(m0, m1, p, st);
+    case HMVIT_GEMM_LIN_CM:
+      p.a_cm = static_cast<const float*>(a->a); p.out_cm = static_cast<float*>(a->out);
+      p.tile_ego_only = a->ego_only ? 1 : 0;
+      return launch_rowgemm<4, PRO_CM_CAST, EPI_CM_STORE>(m0, m1, p, st);
+    case HMVIT_GEMM_LIN_ROWS:
+      p.a_cm = static_cast<const float*>(a->a); p.out_rows = static_cast<__nv_bfloat16*>(a->out);
+      p.tile_ego_only = a->ego_only ? 1 : 0;
+      return launch_rowgemm<4, PRO_CM_CAST, EPI_ROWS_BF16>(m0, m1, p, st);
+    case HMVIT_GEMM_ROWS_LIN_CM:
+      p.a_rows = static_cast<const __nv_bfloat16*>(a->a); p.out_cm = static_cast<float*>(a->out);
+      p.tile_ego_only = a->ego_only ? 1 : 0;
+      if (a->resid != nullptr) return launch_rowgemm<2, PRO_ROWS_BF16, EPI_CM_RESID>(m0, m1, p, st);
+      return launch_rowgemm<2, PRO_ROWS_BF16, EPI_CM_STORE>(m0, m1, p, st);
     default:
       return fail(HMVIT_ERR_ARG, "hmvit: rowgemm: unknown variant");
   }
@@ -224,8 +245,9 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
   p.q = static_cast<const __nv_bfloat16*>(a->q); p.k = static_cast<const __nv_bfloat16*>(a->k);
   p.v = static_cast<const __nv_bfloat16*>(a->v); p.bk = a->bk; p.bv = a->bv; p.bias_table = a->bias_table; p.key_mask = a->key_mask;
   p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.lse = a->lse;
   dim3 grid((a->H / 8) * (a->W / 8) * 2, a->B * a->L);      // x: (token group, head group)
-  if (legacy) group_attn_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  if (legacy || a->lse != nullptr) group_attn_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(p);
   else group_attn_tc_kernel<<<grid, AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
@@ -427,6 +449,123 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
     g.a = hid; g.w[0] = a->head_w2[0]; g.w[1] = a->head_w2[1]; g.bias = a->head_b2; g.out = a->out;
     rc = hmvit_rowgemm(HMVIT_GEMM_HEAD2, &g, stream); if (rc) return rc;
   }
+  return HMVIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward pass
+// ------------------------------------------------------------------------------------------------
+extern "C" int hmvit_bwd_row_stats(const float* x, float* stats, int32_t B, int32_t L, int32_t N, const int32_t* record_len,
+                                   int32_t ego_only, float eps, void* stream) {
+  HMVIT_CHECK_ARG(x && stats && record_len, "bwd_row_stats: null pointer");
+  HMVIT_CHECK_ARG(B > 0 && L > 0 && N > 0 && B * L <= 65535, "bwd_row_stats: bad shape");
+  dim3 grid((N + 127) / 128, B * L);
+  row_stats_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(x, reinterpret_cast<float2*>(stats), L, N, record_len,
+                                                                        ego_only ? 1 : 0, eps);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+extern "C" int hmvit_bwd_layernorm(const float* dz, const float* x, const float* stats, const float* dres, float* dx, int32_t B,
+                                   int32_t L, int32_t N, const int32_t* record_len, int32_t ego_only, void* stream) {
+  HMVIT_CHECK_ARG(dz && x && stats && dres && dx && record_len, "bwd_layernorm: null pointer");
+  HMVIT_CHECK_ARG(B > 0 && L > 0 && N > 0 && B * L <= 65535, "bwd_layernorm: bad shape");
+  dim3 grid((N + 127) / 128, B * L);
+  ln_bwd_cm_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(dz, x, reinterpret_cast<const float2*>(stats), dres, dx, L, N,
+                                                                        record_len, ego_only ? 1 : 0);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+static int flat_grid(size_t n4) {
+  const size_t blocks = (n4 + 255) / 256;
+  const size_t cap = static_cast<size_t>(num_sms()) * 16;
+  return static_cast<int>(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+extern "C" int hmvit_bwd_gelu(float* hp, float* dh, size_t n, void* stream) {
+  HMVIT_CHECK_ARG(hp && dh, "bwd_gelu: null pointer");
+  HMVIT_CHECK_ARG(n % 4 == 0, "bwd_gelu: n must be a multiple of 4");
+  if (n == 0) return HMVIT_OK;
+  gelu_bwd_kernel<<<flat_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float4*>(hp), reinterpret_cast<float4*>(dh), n / 4);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+extern "C" int hmvit_bwd_cast_bf16(const float* src, void* dst, size_t n, void* stream) {
+  HMVIT_CHECK_ARG(src && dst, "bwd_cast_bf16: null pointer");
+  HMVIT_CHECK_ARG(n % 4 == 0, "bwd_cast_bf16: n must be a multiple of 4");
+  if (n == 0) return HMVIT_OK;
+  cast_bf16_kernel<<<flat_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), n / 4);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+extern "C" int hmvit_bwd_colsum(const void* y, int32_t rows_bf16, float* db, int32_t db_stride, int32_t B, int32_t L, int32_t N,
+                                const int32_t* mode, const int32_t* record_len, int32_t ego_only, void* stream) {
+  HMVIT_CHECK_ARG(y && db && mode && record_len, "bwd_colsum: null pointer");
+  HMVIT_CHECK_ARG(B > 0 && L > 0 && N > 0 && B * L <= 65535 && db_stride >= 256, "bwd_colsum: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (rows_bf16) {
+    dim3 grid((N + 255) / 256, B * L);
+    colsum_rows_kernel<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(y), db, db_stride, L, N, mode, record_len, ego_only ? 1 : 0);
+  } else {
+    dim3 grid(256 / 8, B * L);
+    colsum_cm_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(y), db, db_stride, L, N, mode, record_len, ego_only ? 1 : 0);
+  }
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+extern "C" int hmvit_bwd_wgrad(const HmvitWgradArgs* a, void* stream) {
+  HMVIT_CHECK_ARG(a != nullptr, "bwd_wgrad: null args");
+  HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->N > 0 && a->B * a->L <= 65535, "bwd_wgrad: bad shape");
+  HMVIT_CHECK_ARG(a->N % 32 == 0, "bwd_wgrad: N must be a multiple of 32");
+  HMVIT_CHECK_ARG(a->mode && a->record_len && a->a && a->b && a->dw, "bwd_wgrad: null pointer");
+  HMVIT_CHECK_ARG(a->dw_rows >= 256 && a->dw_row0 >= 0 && a->dw_row0 + 256 <= a->dw_rows, "bwd_wgrad: bad dw window");
+  HMVIT_CHECK_ARG(!(a->b_stats != nullptr && a->b_rows_bf16), "bwd_wgrad: b_stats needs a cm B operand");
+  WgradParams p;
+  p.L = a->L; p.N = a->N; p.mode = a->mode; p.record_len = a->record_len; p.ego_only = a->ego_only ? 1 : 0;
+  p.a_cm = static_cast<const float*>(a->a); p.a_rows = static_cast<const __nv_bfloat16*>(a->a);
+  p.b_cm = static_cast<const float*>(a->b); p.b_rows = static_cast<const __nv_bfloat16*>(a->b);
+  p.b_stats = reinterpret_cast<const float2*>(a->b_stats);
+  p.dw = a->dw; p.dw_rows = a->dw_rows; p.dw_row0 = a->dw_row0; p.tok_chunk = 2048;
+  dim3 grid(4, (a->N + p.tok_chunk - 1) / p.tok_chunk, a->B * a->L);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (a->a_rows_bf16 && a->b_rows_bf16) wgrad_kernel<true, true><<<grid, 256, 0, st>>>(p);
+  else if (a->a_rows_bf16) wgrad_kernel<true, false><<<grid, 256, 0, st>>>(p);
+  else if (a->b_rows_bf16) wgrad_kernel<false, true><<<grid, 256, 0, st>>>(p);
+  else wgrad_kernel<false, false><<<grid, 256, 0, st>>>(p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+extern "C" int hmvit_group_attn_bwd(const HmvitAttnBwdArgs* a, void* stream) {
+  HMVIT_CHECK_ARG(a != nullptr, "group_attn_bwd: null args");
+  HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->H > 0 && a->W > 0, "group_attn_bwd: bad shape");
+  HMVIT_CHECK_ARG(a->H % 8 == 0 && a->W % 8 == 0, "group_attn_bwd: H and W must be divisible by the window size 8");
+  HMVIT_CHECK_ARG(a->B * a->L <= 65535, "group_attn_bwd: B*L exceeds grid limit");
+  HMVIT_CHECK_ARG(a->kind == 0 || a->kind == 1, "group_attn_bwd: kind must be 0 (window) or 1 (grid)");
+  HMVIT_CHECK_ARG(a->mode && a->record_len && a->cav_mask && a->T && a->q && a->k && a->v && a->bk && a->bv && a->bias_table &&
+                  a->o && a->d_o && a->lse && a->dq && a->dk && a->dv && a->dbk && a->dbv && a->dbias_table,
+                  "group_attn_bwd: null pointer");
+  HMVIT_CHECK_ARG(a->cell > 0.0, "group_attn_bwd: cell size must be positive");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(group_attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnBwdCfg::SMEM_BYTES);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  AttnBwdParams p;
+  p.B = a->B; p.L = a->L; p.H = a->H; p.W = a->W; p.kind = a->kind; p.ego_only = a->ego_only ? 1 : 0;
+  p.mode = a->mode; p.record_len = a->record_len; p.cav_mask = a->cav_mask; p.T = a->T; p.cell = a->cell;
+  p.q = static_cast<const __nv_bfloat16*>(a->q); p.k = static_cast<const __nv_bfloat16*>(a->k);
+  p.v = static_cast<const __nv_bfloat16*>(a->v); p.bk = a->bk; p.bv = a->bv; p.bias_table = a->bias_table;
+  p.o = static_cast<const __nv_bfloat16*>(a->o); p.d_o = static_cast<const __nv_bfloat16*>(a->d_o); p.lse = a->lse;
+  p.dq = a->dq; p.dk = a->dk; p.dv = a->dv; p.dbk = a->dbk; p.dbv = a->dbv; p.dbias_table = a->dbias_table;
+  dim3 grid((a->H / 8) * (a->W / 8) * 2, a->B * a->L);
+  group_attn_bwd_kernel<<<grid, AttnBwdCfg::THREADS, AttnBwdCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }
 

@@ -44,6 +44,7 @@ struct AttnParams {
   const float* bias_table;     // [225][8] relative_position_bias_table.weight
   const uint8_t* key_mask;     // optional [B*L][N]: extra per-token key mask of source j (unit-level API), or null
   __nv_bfloat16* out;          // [B*L*N][256]
+  float* lse;                  // optional [B*L*N][8]: log2-domain log-sum-exp of every (query row, head), saved for the backward
 };
 
 constexpr int kAttnThreads = 128;
@@ -323,6 +324,16 @@ __global__ void __launch_bounds__(kAttnThreads, 4) group_attn_kernel(const AttnP
   }
   }
 
+  // ---- training: save the softmax statistics (log2 domain: running max + log2 of the denominator) ----
+  if (p.lse != nullptr && t == 0) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      int r, c; group_token(p.kind, gy, gx, rb * 16 + g + e * 8, p.H, p.W, r, c);
+      float* dst = p.lse + (static_cast<size_t>(a) * N + r * p.W + c) * kHeads + hgc * kHG;
+#pragma unroll
+      for (int hh = 0; hh < kHG; ++hh) dst[hh] = lrow[hh][e] > 0.f ? mrow[hh][e] + log2f(lrow[hh][e]) : INFINITY;
+    }
+  }
   // ---- normalise, stage in smem (reuse sK), coalesced store ----
   __syncthreads();
 #pragma unroll

@@ -12,8 +12,8 @@ Mirrors, name for name (constructor config, forward signature, state_dict keys a
 so that `net_epoch*.pth` checkpoints load unchanged (prefix `fusion_net.` in the detector).
 
 PyTorch here is plumbing: parameter storage, device memory, streams.  All arithmetic of the forward
-runs in hand-written CUDA kernels; a missing extension raises (no eager fallback).  Round 1 ships the
-forward (inference) path; calling it with grad enabled on trainable parameters raises.
+runs in hand-written CUDA kernels; a missing extension raises (no eager fallback).  With grad enabled the
+module runs the training path (hmvit_b200/training.py: activations saved per stage, hand-written backward).
 """
 from __future__ import annotations
 
@@ -23,7 +23,7 @@ from typing import Dict, Tuple
 import torch
 from torch import nn
 
-from . import _lib, ops
+from . import _lib, ops, training
 
 _NUM_TYPES = 2
 _LOG2E = 1.4426950408889634
@@ -234,8 +234,32 @@ def _check_supported(dim, dim_head, window_size):
 def _require_inference(module: nn.Module):
     if torch.is_grad_enabled() and any(p.requires_grad for p in module.parameters()):
         raise NotImplementedError(
-            "hmvit_b200 round 1 implements the forward (inference) path only: call under torch.no_grad() "
-            "or module.requires_grad_(False); the backward kernels are not built yet")
+            "the unit-level HeteroAttention.forward surface is inference only: call under torch.no_grad(); "
+            "gradients are implemented for HeteroFusionBlock / HeteroFusion (hmvit_b200/training.py)")
+
+
+def _wants_grad(module: nn.Module, x: torch.Tensor) -> bool:
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters()))
+
+
+def _check_dropout(block):
+    # the reference applies Dropout(p) after a_linears and twice in the FFN in train mode (hetero_fusion.py:66,
+    # base_transformer.py:186-190); bit-parity with its RNG is impossible, and the kernels have no dropout yet
+    if block.training and block.drop_out > 0:
+        raise NotImplementedError(
+            f"hmvit_b200 training path: drop_out={block.drop_out} in train mode is not supported -- set drop_out: 0 "
+            "in the yaml or call .eval() (gradients are still computed)")
+
+
+def _check_inputs(block, x):
+    if x.dim() != 5:
+        raise ValueError(f"x: expected (B, L, C, H, W), got {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise ValueError("hmvit_b200 runs on CUDA tensors only (no CPU fallback)")
+    if x.shape[2] != 256:
+        raise ValueError(f"x: channel dim must be 256, got {x.shape[2]}")
+    if x.shape[3] % block.window_size or x.shape[4] % block.window_size:
+        raise ValueError(f"H={x.shape[3]}, W={x.shape[4]} must be divisible by the window size {block.window_size}")
 
 
 class HeteroFusionBlock(nn.Module):
@@ -248,6 +272,7 @@ class HeteroFusionBlock(nn.Module):
         agent_size, window_size = config['agent_size'], config['window_size']
         drop_out, dim_head = config['drop_out'], config['dim_head']
         self.architect_mode = config['architect_mode']
+        self.drop_out = float(drop_out)
         if mlp_dim != input_dim:
             raise ValueError("hmvit_b200 kernels require mlp_dim == input_dim == 256")
         self.spatial_transform = SpatialTransformation(config['spatial_transform'])
@@ -297,7 +322,10 @@ class HeteroFusionBlock(nn.Module):
         padded slots are returned unchanged (the reference leaves discarded values there)."""
         if self.architect_mode != 'sequential':
             raise ValueError(f"{self.architect_mode} not implemented")
-        _require_inference(self)
+        if _wants_grad(self, x):
+            _check_inputs(self, x)
+            _check_dropout(self)
+            return training.fusion_train(ops, self, None, x, pairwise_t_matrix, mode, record_len, mask, num_iters=1)
         xres = x.detach().float().clone().contiguous()
         _run_fusion(self, None, x, pairwise_t_matrix, mode, record_len, mask, num_iters=1, xres=xres)
         return xres
@@ -334,7 +362,11 @@ class HeteroFusion(nn.Module):
         blk = self.hetero_fusion_block
         if blk.architect_mode != 'sequential':
             raise ValueError(f"{blk.architect_mode} not implemented")
-        _require_inference(self)
+        if _wants_grad(self, x):
+            _check_inputs(blk, x)
+            _check_dropout(blk)
+            return training.fusion_train(ops, blk, self, x, pairwise_t_matrix, mode, record_len, mask,
+                                         num_iters=self.num_iters, skip_dead=self.skip_dead_queries)
         return _run_fusion(blk, self, x, pairwise_t_matrix, mode, record_len, mask, num_iters=self.num_iters)
 
 

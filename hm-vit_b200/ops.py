@@ -69,7 +69,7 @@ def out_ffn_chain(*, B, L, N, mode, record_len, o, resid, out, wa0, wa1, ba, w1_
 
 
 def group_attn(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, k, v, bk, bv, bias_table, out,
-               ego_only=False, key_mask=None):
+               ego_only=False, key_mask=None, lse=None):
     args = _lib.AttnArgs()
     args.B, args.L, args.H, args.W = B, L, H, W
     args.kind = kind
@@ -81,8 +81,71 @@ def group_attn(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, k, v
     args.bk, args.bv, args.bias_table = bk.data_ptr(), bv.data_ptr(), bias_table.data_ptr()
     args.key_mask = key_mask.data_ptr() if key_mask is not None else None
     args.out = out.data_ptr()
+    args.lse = lse.data_ptr() if lse is not None else None
     _lib.check(_lib.load().hmvit_group_attn(C.byref(args), _stream()))
     return out
+
+
+# ---- backward pass -------------------------------------------------------------------------------
+def bwd_row_stats(x, stats, *, B, L, N, record_len, ego_only=False, eps=1e-5):
+    """stats[a*N + tok] = (mean, rstd) of the 256 channels of x (cm fp32)."""
+    _lib.check(_lib.load().hmvit_bwd_row_stats(x.data_ptr(), stats.data_ptr(), B, L, N, record_len.data_ptr(),
+                                               1 if ego_only else 0, eps, _stream()))
+    return stats
+
+
+def bwd_layernorm(dz, x, stats, dres, dx, *, B, L, N, record_len, ego_only=False):
+    """dx = dres + rstd (dz - mean(dz) - z mean(dz z)); cm fp32; dx may alias dres."""
+    _lib.check(_lib.load().hmvit_bwd_layernorm(dz.data_ptr(), x.data_ptr(), stats.data_ptr(), dres.data_ptr(), dx.data_ptr(),
+                                               B, L, N, record_len.data_ptr(), 1 if ego_only else 0, _stream()))
+    return dx
+
+
+def bwd_gelu(hp, dh):
+    """in place: hp <- gelu(hp), dh <- dh * gelu'(hp)."""
+    _lib.check(_lib.load().hmvit_bwd_gelu(hp.data_ptr(), dh.data_ptr(), hp.numel(), _stream()))
+
+
+def bwd_cast_bf16(src, dst):
+    _lib.check(_lib.load().hmvit_bwd_cast_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()))
+    return dst
+
+
+def bwd_colsum(y, db, *, B, L, N, mode, record_len, ego_only=False):
+    """db[type] += sum over tokens of y; y cm fp32 (B*L, 256, N) or bf16 rows (B*L*N, 256); db (2, >=256) fp32 view whose
+    first 256 columns are accumulated (row stride = db.stride(0))."""
+    _lib.check(_lib.load().hmvit_bwd_colsum(y.data_ptr(), 1 if y.dtype == torch.bfloat16 else 0, db.data_ptr(), db.stride(0),
+                                            B, L, N, mode.data_ptr(), record_len.data_ptr(), 1 if ego_only else 0, _stream()))
+    return db
+
+
+def bwd_wgrad(a, b, dw, *, B, L, N, mode, record_len, ego_only=False, b_stats=None, row0=0):
+    """dw[type, row0 + m, n] += sum_tok a(tok, m) b(tok, n); a / b: cm fp32 or bf16 rows; dw (2, rows, 256) fp32."""
+    args = _lib.WgradArgs()
+    args.B, args.L, args.N = B, L, N
+    args.mode, args.record_len = mode.data_ptr(), record_len.data_ptr()
+    args.ego_only = 1 if ego_only else 0
+    args.a, args.a_rows_bf16 = a.data_ptr(), 1 if a.dtype == torch.bfloat16 else 0
+    args.b, args.b_rows_bf16 = b.data_ptr(), 1 if b.dtype == torch.bfloat16 else 0
+    args.b_stats = b_stats.data_ptr() if b_stats is not None else None
+    args.dw, args.dw_rows, args.dw_row0 = dw.data_ptr(), dw.shape[1], row0
+    _lib.check(_lib.load().hmvit_bwd_wgrad(C.byref(args), _stream()))
+    return dw
+
+
+def group_attn_bwd(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, k, v, bk, bv, bias_table, o, d_o, lse,
+                   dq, dk, dv, dbk, dbv, dbias_table, ego_only=False):
+    args = _lib.AttnBwdArgs()
+    args.B, args.L, args.H, args.W = B, L, H, W
+    args.kind, args.ego_only = kind, 1 if ego_only else 0
+    args.mode, args.record_len, args.cav_mask = mode.data_ptr(), record_len.data_ptr(), cav_mask.data_ptr()
+    args.T, args.cell = T.data_ptr(), float(cell)
+    args.q, args.k, args.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    args.bk, args.bv, args.bias_table = bk.data_ptr(), bv.data_ptr(), bias_table.data_ptr()
+    args.o, args.d_o, args.lse = o.data_ptr(), d_o.data_ptr(), lse.data_ptr()
+    args.dq, args.dk, args.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    args.dbk, args.dbv, args.dbias_table = dbk.data_ptr(), dbv.data_ptr(), dbias_table.data_ptr()
+    _lib.check(_lib.load().hmvit_group_attn_bwd(C.byref(args), _stream()))
 
 
 def warp_bilinear(x: torch.Tensor, T: torch.Tensor, cell: float) -> torch.Tensor:

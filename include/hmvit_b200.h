@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMVIT_ABI_VERSION 1
+#define HMVIT_ABI_VERSION 2
 
 /* error codes */
 #define HMVIT_OK 0
@@ -52,7 +52,13 @@ enum {
   HMVIT_GEMM_FFN2 = 3,  /* A = hidden cm tf32; out cm = A W^T + bias + resid cm                              */
   HMVIT_GEMM_HEAD1 = 4, /* A = x cm tf32 (slot 0 only, no norm); out cm = tf32(gelu(A W^T + bias))           */
   HMVIT_GEMM_HEAD2 = 5, /* A = hidden cm tf32 (slot 0 only); out [B][256][N] = A W^T + bias                  */
-  HMVIT_GEMM_QKV_NOLN = 6 /* like QKV but A = x cm cast to bf16 without LayerNorm (unit-level attention API)  */
+  HMVIT_GEMM_QKV_NOLN = 6, /* like QKV but A = x cm cast to bf16 without LayerNorm (unit-level attention API) */
+  /* generic typed linears used by the backward pass (dgrad = a linear with the transposed weight) and by the
+     recomputation of forward intermediates; all honour ego_only and write every slot's own rows */
+  HMVIT_GEMM_LN_LIN_CM = 7,   /* A = LN_type(x cm) tf32; out cm = A W^T + bias                                */
+  HMVIT_GEMM_LIN_CM = 8,      /* A = x cm tf32;          out cm = A W^T + bias                                */
+  HMVIT_GEMM_LIN_ROWS = 9,    /* A = x cm tf32;          out rows bf16 [B*L*N][256] = A W^T + bias            */
+  HMVIT_GEMM_ROWS_LIN_CM = 10 /* A = rows bf16;          out cm = A W^T + bias (+ resid cm when resid != NULL) */
 };
 
 typedef struct {
@@ -128,6 +134,8 @@ typedef struct {
   const uint8_t* key_mask;    /* optional [B*L][N] extra key mask indexed by (source slot, TARGET token); NULL = none.
                                  Used by the unit-level HeteroAttention.forward surface (explicit mask argument). */
   void* out;                  /* bf16 rows [B*L*N][256] */
+  float* lse;                 /* optional [B*L*N][8]: log2-domain log-sum-exp per (query token, head), saved for
+                                 hmvit_group_attn_bwd; NULL = not written (inference) */
 } HmvitAttnArgs;
 
 int hmvit_group_attn(const HmvitAttnArgs* args, void* stream);
@@ -188,6 +196,64 @@ size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W);
 int hmvit_fusion_forward(const HmvitFusionArgs* args, void* stream);
 /* number of kernel launches one hmvit_fusion_forward enqueues (for launch accounting) */
 int hmvit_fusion_launch_count(int32_t num_iters, int32_t head);
+
+/* ---- backward pass (training configuration) ---------------------------------------------------------
+ * The reference differentiates the fusion module with autograd (train_camera.py:172-193).  Here the
+ * adjoint of the restructured forward is a set of kernels; the input-gradient GEMMs are hmvit_rowgemm
+ * calls with transposed weights (variants 7-10), everything else is below.  Gradients are produced for
+ * the FOLDED weights and mapped to the module parameters on the host through the folding function.
+ * All calls are typed by mode[], skip padded slots and (ego_only != 0) every slot but 0. */
+
+/* stats[a*N + tok] = (mean, rstd) over the 256 channels of x cm (biased variance, eps inside the sqrt) */
+int hmvit_bwd_row_stats(const float* x, float* stats, int32_t B, int32_t L, int32_t N, const int32_t* record_len,
+                        int32_t ego_only, float eps, void* stream);
+/* LayerNorm (no affine) backward + residual: dx = dres + rstd (dz - mean(dz) - z mean(dz z)), z = (x - mean) rstd.
+ * All cm fp32; dx may alias dres.  Adjoint of HeteroLayerNorm (base_transformer.py:171-177). */
+int hmvit_bwd_layernorm(const float* dz, const float* x, const float* stats, const float* dres, float* dx, int32_t B,
+                        int32_t L, int32_t N, const int32_t* record_len, int32_t ego_only, void* stream);
+/* in place over n floats: hp <- gelu_erf(hp), dh <- dh * gelu_erf'(hp)   (nn.GELU, base_transformer.py:188) */
+int hmvit_bwd_gelu(float* hp, float* dh, size_t n, void* stream);
+/* dst[i] = bf16(src[i]), n floats (n % 4 == 0) */
+int hmvit_bwd_cast_bf16(const float* src, void* dst, size_t n, void* stream);
+/* bias gradient: db[type*db_stride + c] += sum over tokens of y;  y is cm fp32 (rows_bf16 == 0) or bf16 rows */
+int hmvit_bwd_colsum(const void* y, int32_t rows_bf16, float* db, int32_t db_stride, int32_t B, int32_t L, int32_t N,
+                     const int32_t* mode, const int32_t* record_len, int32_t ego_only, void* stream);
+
+/* typed weight gradient  dW[type][row0 + m][n] += sum_tok A(tok, m) B(tok, n)  (m, n < 256), tf32 tensor cores */
+typedef struct {
+  int32_t B, L, N;
+  const int32_t* mode;
+  const int32_t* record_len;
+  int32_t ego_only;
+  const void* a;              /* output-gradient operand: cm fp32, or bf16 rows when a_rows_bf16 != 0 */
+  int32_t a_rows_bf16;
+  const void* b;              /* input-activation operand: cm fp32, or bf16 rows when b_rows_bf16 != 0 */
+  int32_t b_rows_bf16;
+  const float* b_stats;       /* optional (b cm only): [B*L*N][2] (mean, rstd) -- B is normalised on the fly */
+  float* dw;                  /* [2][dw_rows][256] fp32, accumulated */
+  int32_t dw_rows, dw_row0;
+} HmvitWgradArgs;
+int hmvit_bwd_wgrad(const HmvitWgradArgs* args, void* stream);
+
+/* backward of hmvit_group_attn: same geometry arguments; q/k/v/o are the forward tensors, d_o the gradient of the
+ * forward output, lse the statistics saved by the forward.  dq [R][256], dk / dv [2][R][256], dbk / dbv [2][2][256],
+ * dbias_table [225][8]: fp32, ACCUMULATED (zero-fill before the first call).  R = B*L*N. */
+typedef struct {
+  int32_t B, L, H, W;
+  int32_t kind, ego_only;
+  const int32_t* mode;
+  const int32_t* record_len;
+  const int32_t* cav_mask;
+  const float* T;
+  double cell;
+  const void* q; const void* k; const void* v;
+  const float* bk; const float* bv; const float* bias_table;
+  const void* o; const void* d_o;
+  const float* lse;
+  float* dq; float* dk; float* dv;
+  float* dbk; float* dbv; float* dbias_table;
+} HmvitAttnBwdArgs;
+int hmvit_group_attn_bwd(const HmvitAttnBwdArgs* args, void* stream);
 
 /* ---- bring-up / self-test helpers ---------------------------------------------------------------------
  * Writes {dynamic-smem base address & 1023, TMEM base of the first allocation} for diagnostics. */

@@ -522,3 +522,275 @@ def check_ragged_batch():
 
 
 CHECKS.update({"cuda_graph": check_cuda_graph, "ragged_batch": check_ragged_batch})
+
+
+# ----------------------------------------------------------------------------------------------
+# backward / training path: every CUDA kernel against tests/emul_ops.py, then whole-module
+# gradients against torch.autograd through the CPU oracle
+# ----------------------------------------------------------------------------------------------
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import emul_ops as EM  # noqa: E402
+
+
+def _geo_small(seed=7, B=2, L=3, H=16, W=24, record_len=(3, 2)):
+    x, T, md, rl, mask = _scene(B, L, H, W, list(record_len), seed=seed, tx=10, ty=5)
+    return dict(B=B, L=L, H=H, W=W, N=H * W, T=T, mode=md.to(torch.int32), rl=rl.to(torch.int32), cav=mask.to(torch.int32))
+
+
+def _valid_rows(g, t, rows=False, ego_only=False):
+    """select the data of active agents from a cm (B*L, 256, N) or rows (R, 256) tensor"""
+    out = []
+    for b, l, ai in EM._agents(g["B"], g["L"], g["rl"], ego_only):
+        out.append(t[ai * g["N"]:(ai + 1) * g["N"]] if rows else t[ai])
+    return torch.stack(out).float()
+
+
+def check_bwd_small_kernels():
+    """row statistics, LayerNorm backward, GELU backward, bf16 cast, bias column sums vs the torch emulation."""
+    ops = pkg().ops
+    g = _geo_small()
+    B, L, N = g["B"], g["L"], g["N"]
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(B * L, 256, N, generator=gen) * 1.5 + 0.3
+    dz = torch.randn(B * L, 256, N, generator=gen)
+    dres = torch.randn(B * L, 256, N, generator=gen)
+    md, rl = g["mode"].to(DEV), g["rl"].to(DEV)
+    res = {}
+    for ego in (False, True):
+        st_ref = torch.zeros(B * L * N, 2)
+        EM.bwd_row_stats(x, st_ref, B=B, L=L, N=N, record_len=g["rl"], ego_only=ego)
+        st = torch.zeros(B * L * N, 2, device=DEV)
+        ops.bwd_row_stats(x.to(DEV), st, B=B, L=L, N=N, record_len=rl, ego_only=ego)
+        res[f"stats_ego{int(ego)}"] = max_rel(st.cpu(), st_ref)
+        dx_ref = torch.zeros_like(x)
+        EM.bwd_layernorm(dz, x, st_ref, dres, dx_ref, B=B, L=L, N=N, record_len=g["rl"], ego_only=ego)
+        dx = torch.zeros_like(x, device=DEV)
+        ops.bwd_layernorm(dz.to(DEV), x.to(DEV), st, dres.to(DEV), dx, B=B, L=L, N=N, record_len=rl, ego_only=ego)
+        res[f"ln_bwd_ego{int(ego)}"] = rel_l2(dx.cpu(), dx_ref)
+        for rows in (False, True):
+            y = (torch.randn(B * L * N, 256, generator=gen).to(torch.bfloat16) if rows else dz)
+            db_ref = torch.zeros(2, 1280)
+            EM.bwd_colsum(y, db_ref[:, 256:], B=B, L=L, N=N, mode=g["mode"], record_len=g["rl"], ego_only=ego)
+            db = torch.zeros(2, 1280, device=DEV)
+            ops.bwd_colsum(y.to(DEV), db[:, 256:], B=B, L=L, N=N, mode=md, record_len=rl, ego_only=ego)
+            res[f"colsum_rows{int(rows)}_ego{int(ego)}"] = max_rel(db.cpu(), db_ref)
+    hp, dh = torch.randn(B * L, 256, N, generator=gen) * 2, torch.randn(B * L, 256, N, generator=gen)
+    hp_d, dh_d = hp.to(DEV), dh.to(DEV)
+    EM.bwd_gelu(hp, dh)
+    ops.bwd_gelu(hp_d, dh_d)
+    res["gelu_fwd"], res["gelu_bwd"] = max_rel(hp_d.cpu(), hp), max_rel(dh_d.cpu(), dh)
+    src = torch.randn(5, 1000, 256, generator=gen)
+    dst = torch.empty(5, 1000, 256, dtype=torch.bfloat16, device=DEV)
+    ops.bwd_cast_bf16(src.to(DEV), dst)
+    assert torch.equal(dst.cpu(), src.to(torch.bfloat16))
+    torch.cuda.synchronize()
+    assert all(v < 2e-5 for v in res.values()), res
+    return res
+
+
+def check_bwd_wgrad():
+    """typed weight gradient, all four operand-layout combinations (+ on-the-fly normalisation); tf32 operands."""
+    ops = pkg().ops
+    g = _geo_small(seed=8)
+    B, L, N = g["B"], g["L"], g["N"]
+    gen = torch.Generator().manual_seed(2)
+    md, rl = g["mode"].to(DEV), g["rl"].to(DEV)
+    a_cm, b_cm = torch.randn(B * L, 256, N, generator=gen), torch.randn(B * L, 256, N, generator=gen) + 0.5
+    a_rows = torch.randn(B * L * N, 256, generator=gen).to(torch.bfloat16)
+    b_rows = torch.randn(B * L * N, 256, generator=gen).to(torch.bfloat16)
+    st = torch.zeros(B * L * N, 2)
+    EM.bwd_row_stats(b_cm, st, B=B, L=L, N=N, record_len=g["rl"])
+    res = {}
+    for name, a, b, stats, ego in (("cm_cm", a_cm, b_cm, None, False), ("cm_cmln", a_cm, b_cm, st, False),
+                                   ("cm_rows", a_cm, b_rows, None, True), ("rows_cm", a_rows, b_cm, st, False),
+                                   ("rows_rows", a_rows, b_rows, None, False)):
+        ref = torch.zeros(2, 1280, 256)
+        EM.bwd_wgrad(a, b, ref, B=B, L=L, N=N, mode=g["mode"], record_len=g["rl"], ego_only=ego, b_stats=stats, row0=512)
+        dw = torch.zeros(2, 1280, 256, device=DEV)
+        ops.bwd_wgrad(a.to(DEV), b.to(DEV), dw, B=B, L=L, N=N, mode=md, record_len=rl, ego_only=ego,
+                      b_stats=None if stats is None else stats.to(DEV), row0=512)
+        res[name] = rel_l2(dw.cpu(), ref)
+        assert float(dw[:, :512].abs().max()) == 0.0 and float(dw[:, 768:].abs().max()) == 0.0
+    torch.cuda.synchronize()
+    assert all(v < 2e-3 for v in res.values()), res          # tf32 operands (10-bit mantissa), fp32 accumulate
+    return res
+
+
+def check_bwd_lin_variants():
+    """the row-GEMM variants the backward uses (7-10) against the emulation with equally rounded operands."""
+    p = pkg()
+    ops, lib = p.ops, p._lib
+    g = _geo_small(seed=9)
+    B, L, N = g["B"], g["L"], g["N"]
+    gen = torch.Generator().manual_seed(3)
+    md, rl = g["mode"].to(DEV), g["rl"].to(DEV)
+    x = torch.randn(B * L, 256, N, generator=gen)
+    rows = torch.randn(B * L * N, 256, generator=gen).to(torch.bfloat16)
+    w = [torch.randn(256, 256, generator=gen) / 16 for _ in range(2)]
+    bias = torch.randn(2, 256, generator=gen) * 0.1
+    resid = torch.randn(B * L, 256, N, generator=gen)
+    res = {}
+    common = dict(B=B, L=L, N=N, n_out=256)
+    for name, variant, a, wd, kw, ego in (
+            ("ln_lin_cm", lib.GEMM_LN_LIN_CM, x, [tf32(t) for t in w], {}, False),
+            ("lin_cm", lib.GEMM_LIN_CM, x, [tf32(t) for t in w], {}, True),
+            ("lin_rows", lib.GEMM_LIN_ROWS, x, [tf32(t) for t in w], {}, False),
+            ("rows_lin_cm", lib.GEMM_ROWS_LIN_CM, rows, [t.to(torch.bfloat16) for t in w], {}, False),
+            ("rows_lin_cm_resid", lib.GEMM_ROWS_LIN_CM, rows, [t.to(torch.bfloat16) for t in w], {"resid": resid}, True)):
+        to_rows = variant == lib.GEMM_LIN_ROWS
+        ref = torch.zeros(B * L * N, 256) if to_rows else torch.zeros(B * L, 256, N)
+        EM.rowgemm(variant, a=a.float(), w0=wd[0].float(), w1=wd[1].float(), bias=bias, out=ref, mode=g["mode"], record_len=g["rl"],
+                   ego_only=ego, **kw, **common)
+        out = torch.zeros(B * L * N, 256, dtype=torch.bfloat16, device=DEV) if to_rows else torch.zeros(B * L, 256, N, device=DEV)
+        ops.rowgemm(variant, a=a.to(DEV), w0=wd[0].to(DEV), w1=wd[1].to(DEV), bias=bias.to(DEV), out=out, mode=md, record_len=rl,
+                    ego_only=ego, **{k: v.to(DEV) for k, v in kw.items()}, **common)
+        res[name] = rel_l2(out.float().cpu(), ref)
+    torch.cuda.synchronize()
+    assert all(v < 4e-3 for v in res.values()), res          # tf32 / bf16 operand rounding of A inside the kernel
+    return res
+
+
+def _attn_case(kind, ego_only, seed):
+    p = pkg()
+    ops = p.ops
+    g = _geo_small(seed=seed)
+    B, L, H, W, N = g["B"], g["L"], g["H"], g["W"], g["N"]
+    R = B * L * N
+    gen = torch.Generator().manual_seed(seed)
+    q = (torch.randn(R, 256, generator=gen) * 0.6).to(torch.bfloat16)
+    k = (torch.randn(2, R, 256, generator=gen) * 0.6).to(torch.bfloat16)
+    v = torch.randn(2, R, 256, generator=gen).to(torch.bfloat16)
+    bk, bv = torch.randn(2, 2, 256, generator=gen) * 0.1, torch.randn(2, 2, 256, generator=gen) * 0.1
+    table = torch.randn(225, 8, generator=gen)
+    d_o = torch.randn(R, 256, generator=gen).to(torch.bfloat16)
+    geo = dict(B=B, L=L, H=H, W=W, kind=kind, cell=1.6, ego_only=ego_only)
+    cpu = dict(mode=g["mode"], record_len=g["rl"], cav_mask=g["cav"], T=g["T"])
+    dev = {kk: vv.to(DEV).contiguous() for kk, vv in cpu.items()}
+    return ops, g, geo, cpu, dev, (q, k, v, bk, bv, table, d_o)
+
+
+def check_attn_bwd():
+    """attention forward statistics (lse) and the attention backward kernel against autograd of the emulated
+    attention (window and grid partitions, all egos and ego-only)."""
+    res = {}
+    for kind, ego_only, seed in ((0, False, 31), (1, False, 32), (1, True, 33)):
+        ops, g, geo, cpu, dev, (q, k, v, bk, bv, table, d_o) = _attn_case(kind, ego_only, seed)
+        R = g["B"] * g["L"] * g["N"]
+        out = torch.zeros(R, 256, dtype=torch.bfloat16, device=DEV)
+        lse = torch.zeros(R, 8, device=DEV)
+        ops.group_attn(q=q.to(DEV), k=k.to(DEV), v=v.to(DEV), bk=bk.to(DEV), bv=bv.to(DEV), bias_table=table.to(DEV), out=out,
+                       lse=lse, **geo, **dev)
+        out_ref, lse_ref = torch.zeros(R, 256), torch.zeros(R, 8)
+        EM.group_attn(q=q.float(), k=k.float(), v=v.float(), bk=bk, bv=bv, bias_table=table, out=out_ref, lse=lse_ref, **geo, **cpu)
+        tag = f"kind{kind}_ego{int(ego_only)}"
+        res[f"out_{tag}"] = rel_l2(out.float().cpu(), out_ref)
+        res[f"lse_abs_{tag}"] = float((lse.cpu() - lse_ref).abs().max())
+        gd = {n: torch.zeros(s, device=DEV) for n, s in (("dq", (R, 256)), ("dk", (2, R, 256)), ("dv", (2, R, 256)),
+                                                          ("dbk", (2, 2, 256)), ("dbv", (2, 2, 256)), ("dbias_table", (225, 8)))}
+        ops.group_attn_bwd(q=q.to(DEV), k=k.to(DEV), v=v.to(DEV), bk=bk.to(DEV), bv=bv.to(DEV), bias_table=table.to(DEV),
+                           o=out, d_o=d_o.to(DEV), lse=lse, **gd, **geo, **dev)
+        gr = {n: torch.zeros_like(t, device="cpu") for n, t in gd.items()}
+        EM.group_attn_bwd(q=q.float(), k=k.float(), v=v.float(), bk=bk, bv=bv, bias_table=table, o=out_ref, d_o=d_o.float(),
+                          lse=lse_ref, **gr, **geo, **cpu)
+        for n in gd:
+            res[f"{n}_{tag}"] = rel_l2(gd[n].cpu(), gr[n])
+    torch.cuda.synchronize()
+    for n, val in res.items():
+        tol = 0.03 if n.startswith("lse_abs") else 2e-2      # bf16 tap blend, bf16 P / dS operands, fp32 accumulate
+        assert val < tol, (n, val, res)
+    return res
+
+
+def _train_case(B, L, H, W, record_len, seed, mode=None, skip_dead=True):
+    cfg = O.default_config()
+    cfg["hetero_fusion_block"]["drop_out"] = 0.0
+    P = O.synth_state_dict(cfg, 0)
+    net = pkg().HeteroFusion(cfg)
+    net.load_state_dict(P, strict=True)
+    net = net.to(DEV).train()
+    net.skip_dead_queries = skip_dead
+    x, T, md, rl, mask = _scene(B, L, H, W, record_len, seed, mode=mode, tx=10, ty=5)
+    g_out = torch.randn(B, 256, H, W, generator=torch.Generator().manual_seed(seed + 1))
+    # reference: autograd through the CPU oracle
+    Pg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in P.items()}
+    xr = x.clone().requires_grad_(True)
+    y_ref = O.hetero_fusion(xr, T, md, rl, mask, Pg, cfg)
+    names = [k for k, v in Pg.items() if v.is_floating_point()]
+    gs = torch.autograd.grad((y_ref * g_out).sum(), [xr] + [Pg[k] for k in names], allow_unused=True)
+    g_ref = dict(zip(["x"] + names, gs))
+    # CUDA path
+    xd = x.to(DEV).requires_grad_(True)
+    y = net(xd, T.to(DEV), md.to(DEV), rl.to(DEV), mask.to(DEV))
+    (y * g_out.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    res = {"fwd_rel_l2": rel_l2(y.detach().cpu(), y_ref.detach()), "dx_rel_l2": rel_l2(xd.grad.cpu(), g_ref["x"])}
+    worst, worst_name, n_checked = 0.0, "", 0
+    gnorm = max(float(v.norm()) for k, v in g_ref.items() if v is not None and k != "x")
+    for name, prm in net.named_parameters():
+        ref = g_ref.get(name)
+        if ref is None or "aggregate_fc" in name:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
+            continue
+        if float(ref.norm()) < 1e-4 * gnorm:                 # absent modality / negligible: absolute check
+            assert prm.grad is None or float((prm.grad.cpu() - ref).norm()) < 1e-3 * gnorm, name
+            continue
+        e = rel_l2(prm.grad.cpu(), ref)
+        n_checked += 1
+        if e > worst:
+            worst, worst_name = e, name
+    res.update({"param_worst_rel_l2": worst, "param_worst": worst_name, "params_checked": n_checked})
+    return res
+
+
+def check_train_grads_small():
+    """Whole-module gradients (dL/dx and dL/dtheta of every used parameter) of the CUDA training path against
+    torch.autograd through the fp32 CPU oracle.  Stated tolerance (bf16 / tf32 operands, fp32 accumulate):
+    rel-L2 <= 3e-2 per tensor; the forward output keeps the inference tolerance 1e-3."""
+    res = {}
+    for tag, args in (("mixed", dict(B=2, L=3, H=16, W=24, record_len=[3, 2], seed=41)),
+                      ("nodead", dict(B=1, L=3, H=16, W=24, record_len=[3], seed=42, skip_dead=False)),
+                      ("lidar_ego", dict(B=1, L=4, H=32, W=48, record_len=[4], seed=43, mode=[[1, 0, 0, 1]]))):
+        r = _train_case(**args)
+        res.update({f"{tag}_{k}": v for k, v in r.items()})
+        assert r["fwd_rel_l2"] < 1e-3 and r["dx_rel_l2"] < 3e-2 and r["param_worst_rel_l2"] < 3e-2 and r["params_checked"] > 30, res
+    return res
+
+
+def check_train_api():
+    """grad-mode dispatch of the module surface: dropout in train mode raises, eval + grad works, no_grad is the
+    inference path, the block alone is differentiable, parameters without requires_grad get no gradient."""
+    cfg = O.default_config()
+    P = O.synth_state_dict(cfg, 0)
+    net = pkg().HeteroFusion(cfg)
+    net.load_state_dict(P, strict=True)
+    net = net.to(DEV)
+    x, T, md, rl, mask = _scene(1, 2, 16, 16, [2], 3, tx=5, ty=5)
+    args = [t.to(DEV) for t in (T, md, rl, mask)]
+    net.train()
+    try:
+        net(x.to(DEV), *args)
+        raise AssertionError("drop_out=0.1 in train mode must raise")
+    except NotImplementedError:
+        pass
+    net.eval()
+    with torch.no_grad():
+        y0 = net(x.to(DEV), *args)
+    y1 = net(x.to(DEV), *args)
+    assert y1.requires_grad
+    d = rel_l2(y1.detach().cpu(), y0.cpu())
+    for prm in net.mlp_head.parameters():
+        prm.requires_grad_(False)
+    y1.sum().backward()
+    assert all(prm.grad is None for prm in net.mlp_head.parameters())
+    assert net.hetero_fusion_block.window_attention.relation_att.grad is not None
+    xb = x.to(DEV).requires_grad_(True)
+    yb = net.hetero_fusion_block(xb, *args)
+    yb.square().mean().backward()
+    assert xb.grad is not None and torch.isfinite(xb.grad).all()
+    assert d < 1e-3, d
+    return {"train_vs_infer_fwd_rel_l2": d}
+
+
+CHECKS.update({"bwd_small_kernels": check_bwd_small_kernels, "bwd_wgrad": check_bwd_wgrad,
+               "bwd_lin_variants": check_bwd_lin_variants, "attn_bwd": check_attn_bwd,
+               "train_grads_small": check_train_grads_small, "train_api": check_train_api})
