@@ -83,6 +83,15 @@ def clocks_summary(samples):
 
 
 # ---------------------------------------------------------------------------------------------
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full
+    capture of this same command (profiles/r1_traffic.json, written by tools/ncu_traffic.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(path):
+        return None
+    return json.load(open(path)).get(kernel, {}).get("dram_bytes_per_launch")
+
+
 def make_inputs(seed, batch, record_len=None):
     from oracle import hmvit_oracle as O
     rl = record_len if record_len is not None else [L] * batch
@@ -184,6 +193,58 @@ def kernel_breakdown(pkg, net, inp, iters=3):
     return res
 
 
+def train_step_bench(pkg, dev, dist, world, rank, Bq, steps, warmup=2):
+    """BASELINE config 4: one data-parallel training step of the fusion module = forward with saved activations +
+    hand-written backward on this rank's scenes, then ONE flat-bucket NCCL all-reduce of the parameter gradients."""
+    from oracle import hmvit_oracle as O
+    cfg = O.default_config()
+    cfg["hetero_fusion_block"]["drop_out"] = 0.0            # the kernels have no dropout; parity is stated at p = 0
+    net = pkg.HeteroFusion(cfg).train()
+    net.load_state_dict(O.synth_state_dict(cfg, 0), strict=True)
+    net = net.to(dev)
+    x, T, mode, rl, mask = make_inputs(1234 + 4 + 1000 * rank, Bq)
+    xd = x.to(dev).requires_grad_(True)
+    inp = [t.to(dev) for t in (T, mode, rl, mask)]
+    g = torch.randn(Bq, C, H, W, device=dev)
+    bucket = pkg.FlatGradAllReduce(net)
+
+    def step():
+        for p in net.parameters():
+            p.grad = None
+        xd.grad = None
+        y = net(xd, *inp)
+        (y * g).sum().backward()
+        bucket.allreduce(dist)
+
+    for _ in range(warmup):
+        step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / steps
+    peak = torch.cuda.max_memory_allocated(dev) / 2**30
+    bucket_bytes = bucket.nbytes
+    del net, xd, g, bucket
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE config 4: fusion training step (forward + backward, bf16/tf32 operands, drop_out 0), "
+                        f"{Bq} scenes x 5 agents per GPU, flat-bucket NCCL gradient all-reduce",
+            "value": Bq * world / (ms * 1e-3), "unit": "scenes/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "allreduce_bytes_per_step": 0 if world == 1 else bucket_bytes,
+            "peak_mem_gib": round(peak, 2)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,6 +253,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="scenes per GPU per step")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-4 training-step measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -286,6 +348,9 @@ def main():
         stop.set()
         th.join(timeout=2)
         kern = kernel_breakdown(pkg, net, dev_in) if rank == 0 else None
+    train = None
+    if not args.no_train:
+        train = train_step_bench(pkg, dev, dist, world, rank, Bq, steps=max(2, min(args.steps, 5)))
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -322,7 +387,7 @@ def main():
         alg = (per_full * (launches - 1) + per_dead) / launches if net.skip_dead_queries else per_full
         achieved = alg / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": None, "peak_source": src,
+                "traffic": ncu_traffic("group_attn_kernel"), "peak_source": src,
                 "note": "algorithmic bytes = Q + K' + V' read once + O written, bf16 (DESIGN.md); the kernel is "
                         "gather (L2->SM) bound, its tensor work is 2*2*Lv*N*(Lv*64)*2C FLOP per scene"}
     else:
@@ -330,7 +395,8 @@ def main():
         f = {"ln_qkv_gemm": sf["qkv"], "out_ffn_chain": sf["out"] + sf["ffn"], "head_gemm": sf["ffn"] / Lv / 2}[dom] * Bq
         achieved = f / (kern[dom]["ms_per_launch"] * 1e-3) / 1e12
         roof = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tf_sus, "unit": "TFLOP/s",
-                "frac": achieved / tf_sus, "traffic": None, "peak_source": src}
+                "frac": achieved / tf_sus, "peak_source": src,
+                "traffic": ncu_traffic({"ln_qkv_gemm": "qkv_kernel", "out_ffn_chain": "chain_kernel"}.get(dom, dom))}
 
     total_kernel_ms = sum(v["ms_per_step"] for v in kern.values())
     whole_flops = scene_flops(Lv) * Bq * world
@@ -354,6 +420,8 @@ def main():
         "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"],
                         "share": round(v["ms_per_step"] / total_kernel_ms, 4)} for k, v in kern.items()},
     }
+    if train is not None:
+        line["train_step"] = train
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(2, 1)
     elif world == 1:

@@ -3,13 +3,15 @@
 The directory is called `hm-vit_b200` (not importable by name); load it with `hmvit_loader.load()`
 from the repo root, which registers it as the module `hmvit_b200`.
 """
-from . import _lib, ops  # noqa: F401
+from . import _lib, ops, training  # noqa: F401
 from .fusion import (HeteroAttention, HeteroFeedForward, HeteroFusion, HeteroFusionBlock,  # noqa: F401
                      HeteroLayerNorm, HeteroPreNormResidual, SpatialTransformation,
                      get_roi_and_cav_mask, regroup)
 from .build import build_extension  # noqa: F401
 from .sharding import max_over_ranks, scene_shard  # noqa: F401
+from .distributed import FlatGradAllReduce  # noqa: F401
+from .distributed import FlatGradAllReduce  # noqa: F401
 
 __all__ = ["HeteroFusion", "HeteroFusionBlock", "HeteroAttention", "HeteroLayerNorm", "HeteroFeedForward",
            "HeteroPreNormResidual", "SpatialTransformation", "get_roi_and_cav_mask", "regroup",
-           "build_extension", "ops"]
+           "build_extension", "ops", "training", "FlatGradAllReduce"]

@@ -68,7 +68,8 @@ struct ChainCfg {
   static constexpr int NS = 2;                        // weight ring stages (32 KB each)
   static constexpr int AO_BYTES = 4 * CHUNK;          // O tile, bf16
   static constexpr int PART_BYTES = 4 * 128 * 8;      // per-group partial LN statistics
-  static constexpr int SMEM_BYTES = AO_BYTES + NF * CHUNK + NS * WSTAGE + PART_BYTES + 256 + 1024;
+  static constexpr int BIAS_BYTES = 3 * 2 * 256 * 4;   // ba | b1 | b2, both types: read by every transform thread
+  static constexpr int SMEM_BYTES = AO_BYTES + NF * CHUNK + NS * WSTAGE + PART_BYTES + BIAS_BYTES + 256 + 1024;
   static constexpr int NT = 512;                      // transform threads
   static constexpr int THREADS = NT + 64;
 };
@@ -90,7 +91,8 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
   uint8_t* sF = smem + Cfg::AO_BYTES;
   uint8_t* sW = sF + Cfg::NF * Cfg::CHUNK;
   float2* sPart = reinterpret_cast<float2*>(sW + Cfg::NS * Cfg::WSTAGE);  // [4 groups][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sPart) + Cfg::PART_BYTES);
+  float* sBias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sPart) + Cfg::PART_BYTES);   // [3][2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
   uint64_t* w_full = bars;                      // [NS]
   uint64_t* w_empty = w_full + Cfg::NS;         // [NS]
   uint64_t* f_full = w_empty + Cfg::NS;         // [NF]
@@ -112,6 +114,10 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
     fence_mbar_init();
   }
   if (warp == 17) tmem_alloc<512>(tmem_slot);
+  // biases in shared memory (a global load per use showed up as long-scoreboard stalls of the transform warps)
+  for (int e = threadIdx.x; e < 2 * kC; e += Cfg::THREADS) {
+    sBias[e] = __ldg(p.ba + e); sBias[2 * kC + e] = __ldg(p.b1 + e); sBias[4 * kC + e] = __ldg(p.b2 + e);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 1);
       float s0 = 0.f, sum = 0.f, sq = 0.f;
       {
-        const float* bias = p.ba + type * kC + c0;
+        const float* bias = sBias + type * kC + c0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t r[16];
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
           tmem_ld_wait();
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float v = __uint_as_float(r[k]) + __ldg(bias + q * 16 + k) + rv[q * 16 + k];
+            const float v = __uint_as_float(r[k]) + bias[q * 16 + k] + rv[q * 16 + k];
             if (q == 0 && k == 0) s0 = v;
             const float d = v - s0;
             sum += d; sq += d * d;
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
       mbar_wait(d2_full, ti & 1);
       tc_fence_after();
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 4);
-      const float* b1 = p.b1 + type * kC;
+      const float* b1 = sBias + 2 * kC + type * kC;
 #pragma unroll 1
       for (int kk = 0; kk < 2; ++kk) {
         const int kc = 2 * gq + kk;
@@ -240,7 +246,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         tmem_ld32(D2 + lane_base + kc * 32, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(tf32_rn(gelu_erf_fast(__uint_as_float(r[k]) + __ldg(b1 + kc * 32 + k))));
+        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(tf32_rn(gelu_erf_fast(__uint_as_float(r[k]) + b1[kc * 32 + k])));
         mbar_wait(&f_empty[fs], ph ^ 1u);
         uint8_t* dstF = sF + fs * Cfg::CHUNK;
 #pragma unroll
@@ -255,7 +261,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
       mbar_wait(d1_final, ti & 1);
       tc_fence_after();
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 6);
-      const float* b2 = p.b2 + type * kC + c0;
+      const float* b2 = sBias + 4 * kC + type * kC + c0;
       float t0 = 0.f, tsum = 0.f, tsq = 0.f;
       {
         uint32_t r0[32], r1[32];
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         mbar_arrive(d1_free);                      // D1 is in registers: the next tile's projection may start
 #pragma unroll
         for (int k = 0; k < 64; ++k) {
-          const float v = __uint_as_float(k < 32 ? r0[k] : r1[k - 32]) + __ldg(b2 + k);
+          const float v = __uint_as_float(k < 32 ? r0[k] : r1[k - 32]) + b2[k];
           if (k == 0) t0 = v;
           const float d = v - t0;
           tsum += d; tsq += d * d;

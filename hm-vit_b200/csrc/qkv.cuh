@@ -39,7 +39,7 @@ struct QkvCfg {
   static constexpr int CHUNK = 16384;
   static constexpr int NCHA = 4;                       // A chunks (bf16, K = 256)
 #ifndef HMVIT_QKV_NS
-#define HMVIT_QKV_NS 5
+#define HMVIT_QKV_NS 4
 #endif
 #ifndef HMVIT_QKV_ROT
 #define HMVIT_QKV_ROT 1
@@ -51,7 +51,8 @@ struct QkvCfg {
   static constexpr int N_CHUNKS = 10;                  // 1280 / 128
   static constexpr int A_BYTES = NCHA * CHUNK;         // 64 KB per A buffer
   static constexpr int STAGE_BYTES = 4 * 32 * 128;     // epilogue staging: 4 warps x 32 rows x 128 B (64 columns)
-  static constexpr int SMEM_BYTES = 2 * A_BYTES + NS * CHUNK + STAGE_BYTES + 256 + 1024;
+  static constexpr int BIAS_BYTES = 2 * N_CHUNKS * BN * 4; // both types' [1280] biases, read by every epilogue thread
+  static constexpr int SMEM_BYTES = 2 * A_BYTES + NS * CHUNK + STAGE_BYTES + BIAS_BYTES + 256 + 1024;
   static constexpr int THREADS = 320;
   static constexpr uint32_t TMEM_COLS = 256;
 };
@@ -65,7 +66,8 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
   uint8_t* sA = smem;                                   // [2][A_BYTES]
   uint8_t* sB = sA + 2 * Cfg::A_BYTES;                  // [NS][CHUNK]
   uint8_t* sStage = sB + Cfg::NS * Cfg::CHUNK;          // [4][32][256 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGE_BYTES);
+  float* sBias = reinterpret_cast<float*>(sStage + Cfg::STAGE_BYTES);   // [2][1280]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGE_BYTES + Cfg::BIAS_BYTES);
   uint64_t* b_full = bars;                  // [NS]
   uint64_t* b_empty = b_full + Cfg::NS;     // [NS]
   uint64_t* acc_full = b_empty + Cfg::NS;   // [2]
@@ -84,6 +86,8 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
     fence_mbar_init();
   }
   if (warp == 5) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  // biases live in shared memory: a global (L2) load per use stalled the epilogue warps (ncu: long scoreboard)
+  for (int e = threadIdx.x; e < 2 * Cfg::N_CHUNKS * Cfg::BN; e += Cfg::THREADS) sBias[e] = __ldg(p.bias + e);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -131,25 +135,27 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         const uint32_t buf = ci & 1u;
         mbar_wait(&acc_full[buf], (ci >> 1) & 1u);
         tc_fence_after();
-        const float* bias = p.bias + type * (Cfg::N_CHUNKS * Cfg::BN) + c * Cfg::BN;
+        const float* bias = sBias + type * (Cfg::N_CHUNKS * Cfg::BN) + c * Cfg::BN;
         __nv_bfloat16* obase = p.out_rows + (static_cast<size_t>(c >> 1) * rows_total + static_cast<size_t>(a) * p.N + tok0 + warp * 32) * kC +
                                (c & 1) * Cfg::BN;
-#pragma unroll 1
+        // the whole 128-column accumulator row goes to registers in one batch of TMEM loads, so the MMA warp gets
+        // the buffer back before the (longer) convert / stage / store part starts
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN, r0);
+        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + 32, r1);
+        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + 64, r2);
+        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + 96, r3);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+#pragma unroll
         for (int half = 0; half < 2; ++half) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + half * 64, r0);
-          tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + half * 64 + 32, r1);
-          tmem_ld_wait();
-          if (half == 1) {                        // both halves are in registers: the MMA warp may refill the buffer
-            tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
-          }
           const float* bb = bias + half * 64;
 #pragma unroll
           for (int k8 = 0; k8 < 8; ++k8) {
-            const uint32_t* r = (k8 < 4) ? (r0 + k8 * 8) : (r1 + (k8 - 4) * 8);
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bb + k8 * 8));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bb + k8 * 8 + 4));
+            const uint32_t* r = half == 0 ? ((k8 < 4) ? (r0 + k8 * 8) : (r1 + (k8 - 4) * 8)) : ((k8 < 4) ? (r2 + k8 * 8) : (r3 + (k8 - 4) * 8));
+            const float4 b0 = *reinterpret_cast<const float4*>(bb + k8 * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bb + k8 * 8 + 4);
             uint4 pk;
             pk.x = pack_bf16x2(__uint_as_float(r[0]) + b0.x, __uint_as_float(r[1]) + b0.y);
             pk.y = pack_bf16x2(__uint_as_float(r[2]) + b0.z, __uint_as_float(r[3]) + b0.w);

@@ -4,7 +4,7 @@ ncu's CSV source page is SASS-level without line numbers; nvdisasm -g of the sam
 `//## File "...", line N` markers.  Both list the kernel's instructions in the same order, so they are
 joined by position.
 
-  python tools/ncu_lines.py gpurun_out/prof.ncu-rep group_attn_kernel [launch_skip] [top]
+  python tools/ncu_lines.py gpurun_out/prof.ncu-rep group_attn_kernel [launch_skip] [top] [mangled section pattern]
 """
 import csv
 import os
@@ -50,7 +50,7 @@ def main():
     k = int(skip)
     hdr = rows[starts[k] + 1]
     data = rows[starts[k] + 2:starts[k + 1]]
-    sl = sass_lines(kern)
+    sl = sass_lines(sys.argv[5] if len(sys.argv) > 5 else kern)   # optional: mangled-name pattern of the instance
     if len(sl) != len(data):
         print(f"warning: {len(sl)} disassembled instructions vs {len(data)} profiled rows; joining by position anyway")
     i_s, i_e = hdr.index("# Samples"), hdr.index("Instructions Executed")
