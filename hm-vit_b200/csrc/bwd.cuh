@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const __nv_bfloat16* _
 // typed weight gradient:  dW[type][m][n] += sum_tok A(tok, m) B(tok, n),   m, n in [0, 256)
 // over the tokens of every active agent of that type.  Operands come either from a cm tensor
 // (fp32 [a][256][N], optionally normalised on the fly with per-token (mean, rstd)) or from bf16 rows.
-// Warp-level tensor-core tiles (wmma tf32 m16n16k8, fp32 accumulate): one CTA = a 128 x 128 tile of dW
+// Warp-level tensor-core tiles (wmma bf16 m16n16k16, fp32 accumulate): one CTA = a 128 x 128 tile of dW
 // over a chunk of tokens of one agent, partial sums reduced with fp32 atomics.
 // ------------------------------------------------------------------------------------------
 struct WgradParams {
@@ -159,13 +159,70 @@ struct WgradParams {
   int tok_chunk;                  // tokens per CTA (multiple of 32)
 };
 
-constexpr int kWgKT = 32;                       // tokens per K step
-constexpr int kWgLdK = kWgKT + 4;               // [128][36]  (cm source: k contiguous)
-constexpr int kWgLdM = 128 + 4;                 // [32][132]  (rows source: m contiguous)
-constexpr int kWgTile = 128 * kWgLdK;           // floats per operand tile (>= 32 * 132)
+// Operands are converted to bf16 while they are staged (fp32 accumulate): half the shared-memory traffic and
+// twice the tensor-core rate of tf32 fragments.  The next K tile is prefetched into registers while the current
+// one is multiplied (two shared-memory buffers, one barrier per tile).
+constexpr int kWgKT = 32;                       // tokens per K tile
+constexpr int kWgLdK = kWgKT + 8;               // [128][40] bf16  (cm source: k contiguous)
+constexpr int kWgLdM = 128 + 8;                 // [32][136] bf16  (rows source: m contiguous)
+constexpr int kWgTile = 128 * kWgLdK;           // bf16 elements per operand tile (5120 >= 32 * 136 = 4352)
 
+template <bool ROWS>
+struct WgStage {                                // register image of one operand tile: 128 x 32 elements
+  uint4 v[ROWS ? 2 : 4];                        // rows: 2 x 8 bf16 per thread; cm: 4 x float4 per thread
+  float4 st[2];                                 // cm + stats: (mean, rstd) of this thread's 4 tokens (the same for its 4 rows)
+};
+
+template <bool ROWS>
+HMVIT_DEVINL void wg_load(WgStage<ROWS>& r, const float* cm, const __nv_bfloat16* rows, const float2* stats, int a, int N, int c0,
+                          int tok0, int tid) {
+  if constexpr (ROWS) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = tid + i * 256, k = e >> 4, u = e & 15;
+      r.v[i] = __ldg(reinterpret_cast<const uint4*>(rows + (static_cast<size_t>(a) * N + tok0 + k) * kC + c0) + u);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256, m = e >> 3, u = e & 7;
+      const float4 f = __ldg(reinterpret_cast<const float4*>(cm + (static_cast<size_t>(a) * kC + c0 + m) * N + tok0) + u);
+      r.v[i] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z), __float_as_uint(f.w));
+      if (i == 0 && stats != nullptr) {           // u = tid & 7 for every i: one pair of loads per tile
+        const float4* sp = reinterpret_cast<const float4*>(stats + static_cast<size_t>(a) * N + tok0 + u * 4);
+        r.st[0] = __ldg(sp); r.st[1] = __ldg(sp + 1);
+      }
+    }
+  }
+}
+
+template <bool ROWS>
+HMVIT_DEVINL void wg_store(const WgStage<ROWS>& r, __nv_bfloat16* sm, bool has_stats, int tid) {
+  if constexpr (ROWS) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int e = tid + i * 256, k = e >> 4, u = e & 15;
+      *reinterpret_cast<uint4*>(sm + k * kWgLdM + u * 8) = r.v[i];                 // sm[k][m]
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = tid + i * 256, m = e >> 3, u = e & 7;
+      float x0 = __uint_as_float(r.v[i].x), x1 = __uint_as_float(r.v[i].y), x2 = __uint_as_float(r.v[i].z), x3 = __uint_as_float(r.v[i].w);
+      if (has_stats) {
+        const float4 s01 = r.st[0], s23 = r.st[1];
+        x0 = (x0 - s01.x) * s01.y; x1 = (x1 - s01.z) * s01.w; x2 = (x2 - s23.x) * s23.y; x3 = (x3 - s23.z) * s23.w;
+      }
+      *reinterpret_cast<uint2*>(sm + m * kWgLdK + u * 4) = make_uint2(pack_bf16x2(x0, x1), pack_bf16x2(x2, x3));   // sm[m][k]
+    }
+  }
+}
+
+#ifndef HMVIT_WG_MINB
+#define HMVIT_WG_MINB 1
+#endif
 template <bool A_ROWS, bool B_ROWS>
-__global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p) {
+__global__ void __launch_bounds__(256, HMVIT_WG_MINB) wgrad_kernel(const WgradParams p) {
   using namespace nvcuda;
   const int a = blockIdx.z;
   if (!agent_active(a, p.L, p.record_len, p.ego_only)) return;
@@ -175,88 +232,55 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p) {
   const int tok_end = min(p.N, tok_begin + p.tok_chunk);
   if (tok_begin >= tok_end) return;
 
-  __shared__ __align__(128) float sA[kWgTile];
-  __shared__ __align__(128) float sB[kWgTile];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ __align__(128) __nv_bfloat16 sA[2][kWgTile];
+  __shared__ __align__(128) __nv_bfloat16 sB[2][kWgTile];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;      // warp tile: 64 (m) x 32 (n)
+  const bool has_stats = !B_ROWS && p.b_stats != nullptr;
 
-  wmma::fragment<wmma::accumulator, 16, 16, 8, float> acc[4][2];
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> acc[4][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 2; ++j) wmma::fill_fragment(acc[i][j], 0.f);
 
-  for (int tok0 = tok_begin; tok0 < tok_end; tok0 += kWgKT) {
-    // ---- stage A: 128 (m) x 32 (tok) ----
-    if constexpr (A_ROWS) {
-      // rows [tok][256]: 32 tokens x 16 uint4 (8 channels each) -> sA[k][m]
-      for (int e = threadIdx.x; e < 32 * 16; e += 256) {
-        const int k = e >> 4, u = e & 15;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.a_rows + (static_cast<size_t>(a) * p.N + tok0 + k) * kC + m0) + u);
-        float* d = sA + k * kWgLdM + u * 8;
-        d[0] = bf16_lo(v.x); d[1] = bf16_hi(v.x); d[2] = bf16_lo(v.y); d[3] = bf16_hi(v.y);
-        d[4] = bf16_lo(v.z); d[5] = bf16_hi(v.z); d[6] = bf16_lo(v.w); d[7] = bf16_hi(v.w);
-      }
-    } else {
-      // cm [256][N]: 128 channel rows x 8 float4 -> sA[m][k]
-      for (int e = threadIdx.x; e < 128 * 8; e += 256) {
-        const int m = e >> 3, u = e & 7;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p.a_cm + (static_cast<size_t>(a) * kC + m0 + m) * p.N + tok0) + u);
-        *reinterpret_cast<float4*>(sA + m * kWgLdK + u * 4) = v;
-      }
+  WgStage<A_ROWS> ra;
+  WgStage<B_ROWS> rb;
+  wg_load<A_ROWS>(ra, p.a_cm, p.a_rows, nullptr, a, p.N, m0, tok_begin, tid);
+  wg_load<B_ROWS>(rb, p.b_cm, p.b_rows, p.b_stats, a, p.N, n0, tok_begin, tid);
+  int buf = 0;
+  for (int tok0 = tok_begin; tok0 < tok_end; tok0 += kWgKT, buf ^= 1) {
+    wg_store<A_ROWS>(ra, sA[buf], false, tid);
+    wg_store<B_ROWS>(rb, sB[buf], has_stats, tid);
+    __syncthreads();                       // tile `buf` is complete; every warp is past its reads of tile buf (2 tiles ago)
+    if (tok0 + kWgKT < tok_end) {          // prefetch the next tile into registers while this one is multiplied
+      wg_load<A_ROWS>(ra, p.a_cm, p.a_rows, nullptr, a, p.N, m0, tok0 + kWgKT, tid);
+      wg_load<B_ROWS>(rb, p.b_cm, p.b_rows, p.b_stats, a, p.N, n0, tok0 + kWgKT, tid);
     }
-    // ---- stage B: 128 (n) x 32 (tok) ----
-    if constexpr (B_ROWS) {
-      for (int e = threadIdx.x; e < 32 * 16; e += 256) {
-        const int k = e >> 4, u = e & 15;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.b_rows + (static_cast<size_t>(a) * p.N + tok0 + k) * kC + n0) + u);
-        float* d = sB + k * kWgLdM + u * 8;
-        d[0] = bf16_lo(v.x); d[1] = bf16_hi(v.x); d[2] = bf16_lo(v.y); d[3] = bf16_hi(v.y);
-        d[4] = bf16_lo(v.z); d[5] = bf16_hi(v.z); d[6] = bf16_lo(v.w); d[7] = bf16_hi(v.w);
-      }
-    } else {
-      for (int e = threadIdx.x; e < 128 * 8; e += 256) {
-        const int n = e >> 3, u = e & 7;
-        float4 v = __ldg(reinterpret_cast<const float4*>(p.b_cm + (static_cast<size_t>(a) * kC + n0 + n) * p.N + tok0) + u);
-        if (p.b_stats != nullptr) {
-          const float4 s01 = __ldg(reinterpret_cast<const float4*>(p.b_stats + static_cast<size_t>(a) * p.N + tok0 + u * 4));
-          const float4 s23 = __ldg(reinterpret_cast<const float4*>(p.b_stats + static_cast<size_t>(a) * p.N + tok0 + u * 4) + 1);
-          v.x = (v.x - s01.x) * s01.y; v.y = (v.y - s01.z) * s01.w;
-          v.z = (v.z - s23.x) * s23.y; v.w = (v.w - s23.z) * s23.w;
-        }
-        *reinterpret_cast<float4*>(sB + n * kWgLdK + u * 4) = v;
-      }
-    }
-    __syncthreads();
-    // ---- tensor-core phase: 4 k-steps of 8 tokens ----
+    const __nv_bfloat16* tA = sA[buf];
+    const __nv_bfloat16* tB = sB[buf];
 #pragma unroll
-    for (int kk = 0; kk < kWgKT; kk += 8) {
-      wmma::fragment<wmma::matrix_a, 16, 16, 8, wmma::precision::tf32, typename std::conditional<A_ROWS, wmma::col_major, wmma::row_major>::type> fa[4];
-      wmma::fragment<wmma::matrix_b, 16, 16, 8, wmma::precision::tf32, typename std::conditional<B_ROWS, wmma::row_major, wmma::col_major>::type> fb[2];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if constexpr (A_ROWS) wmma::load_matrix_sync(fa[i], sA + kk * kWgLdM + wm + i * 16, kWgLdM);
-        else wmma::load_matrix_sync(fa[i], sA + (wm + i * 16) * kWgLdK + kk, kWgLdK);
-#pragma unroll
-        for (int t = 0; t < fa[i].num_elements; ++t) fa[i].x[t] = wmma::__float_to_tf32(fa[i].x[t]);
-      }
+    for (int kk = 0; kk < kWgKT; kk += 16) {
+      wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, typename std::conditional<B_ROWS, wmma::row_major, wmma::col_major>::type> fb[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        if constexpr (B_ROWS) wmma::load_matrix_sync(fb[j], sB + kk * kWgLdM + wn + j * 16, kWgLdM);
-        else wmma::load_matrix_sync(fb[j], sB + (wn + j * 16) * kWgLdK + kk, kWgLdK);
-#pragma unroll
-        for (int t = 0; t < fb[j].num_elements; ++t) fb[j].x[t] = wmma::__float_to_tf32(fb[j].x[t]);
+        if constexpr (B_ROWS) wmma::load_matrix_sync(fb[j], tB + kk * kWgLdM + wn + j * 16, kWgLdM);
+        else wmma::load_matrix_sync(fb[j], tB + (wn + j * 16) * kWgLdK + kk, kWgLdK);
       }
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) {          // one A fragment live at a time (register budget: 2 CTAs / SM)
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, typename std::conditional<A_ROWS, wmma::col_major, wmma::row_major>::type> fa;
+        if constexpr (A_ROWS) wmma::load_matrix_sync(fa, tA + kk * kWgLdM + wm + i * 16, kWgLdM);
+        else wmma::load_matrix_sync(fa, tA + (wm + i * 16) * kWgLdK + kk, kWgLdK);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) wmma::mma_sync(acc[i][j], fa[i], fb[j], acc[i][j]);
+        for (int j = 0; j < 2; ++j) wmma::mma_sync(acc[i][j], fa, fb[j], acc[i][j]);
+      }
     }
-    __syncthreads();
   }
+  __syncthreads();
 
-  // ---- epilogue: fragment -> per-warp 16 x 16 patch in smem -> coalesced fp32 atomics ----
-  float* patch = sA + warp * 256;                  // sA is free after the final __syncthreads
+  // ---- epilogue: fragment -> per-warp 16 x 16 fp32 patch in smem -> coalesced fp32 atomics ----
+  float* patch = reinterpret_cast<float*>(&sA[0][0]) + warp * 256;      // 8 KB of the 20 KB of sA
   float* dst = p.dw + (static_cast<size_t>(type) * p.dw_rows + p.dw_row0 + m0 + wm) * kC + n0 + wn;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

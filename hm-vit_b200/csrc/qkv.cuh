@@ -6,12 +6,12 @@
 // (hetero_fusion.py:111-140) + get_hetero_edge_weights (:154-185; relation_att / relation_msg are
 // folded into W_k / W_v on the host) for every valid agent of every scene in one launch.
 //
-// One CTA per SM loops over 128-token tiles.  Warp roles (10 warps):
-//   warps 6-9  A producers: typed LayerNorm of the NEXT tile (channel-major fp32 -> bf16, UMMA
+// One CTA per SM loops over 128-token tiles.  Warp roles (14 warps; numbering in QkvCfg):
+//   4 warps    A producers: typed LayerNorm of the NEXT tile (channel-major fp32 -> bf16, UMMA
 //              SWIZZLE_128B layout) into one of two A buffers, overlapped with the current tile's MMAs
-//   warp 4     TMA producer: weight stages (128 output channels x 128 B of K), 3-deep ring
-//   warp 5     MMA issuer: 16 x tcgen05.mma (M128 N128 K16) per 128-column chunk, 2 TMEM buffers
-//   warps 0-3  epilogue: TMEM -> +bias -> bf16 -> swizzled smem staging -> fully coalesced row stores
+//   1 warp     TMA producer: weight stages (128 output channels x 128 B of K), 3-deep ring
+//   1 warp     MMA issuer: 16 x tcgen05.mma (M128 N128 K16) per 128-column chunk, 2 TMEM buffers
+//   warps 0-7  epilogue: TMEM -> +bias -> bf16 -> swizzled smem staging -> fully coalesced row stores
 // Only the chunks a scene needs are computed (K'/V' for the ego types present; in the last stage Q
 // for slot 0 only).
 #pragma once
@@ -39,7 +39,7 @@ struct QkvCfg {
   static constexpr int CHUNK = 16384;
   static constexpr int NCHA = 4;                       // A chunks (bf16, K = 256)
 #ifndef HMVIT_QKV_NS
-#define HMVIT_QKV_NS 4
+#define HMVIT_QKV_NS 3
 #endif
 #ifndef HMVIT_QKV_ROT
 #define HMVIT_QKV_ROT 1
@@ -50,15 +50,27 @@ struct QkvCfg {
   static constexpr int NS = HMVIT_QKV_NS;              // weight ring stages
   static constexpr int N_CHUNKS = 10;                  // 1280 / 128
   static constexpr int A_BYTES = NCHA * CHUNK;         // 64 KB per A buffer
-  static constexpr int STAGE_BYTES = 4 * 32 * 128;     // epilogue staging: 4 warps x 32 rows x 128 B (64 columns)
+  static constexpr int EPI_WARPS = 8;                  // 2 per SM sub-partition: (TMEM lane quarter, 64-column half of the chunk)
+  static constexpr int STAGE_BYTES = EPI_WARPS * 32 * 128;   // epilogue staging: per warp 32 rows x 128 B (64 columns)
   static constexpr int BIAS_BYTES = 2 * N_CHUNKS * BN * 4; // both types' [1280] biases, read by every epilogue thread
-  static constexpr int SMEM_BYTES = 2 * A_BYTES + NS * CHUNK + STAGE_BYTES + BIAS_BYTES + 256 + 1024;
-  static constexpr int THREADS = 320;
-  static constexpr uint32_t TMEM_COLS = 256;
+  static constexpr int PART_BYTES = 2 * 128 * 8;       // partial LayerNorm sums exchanged between the two threads of a row
+  static constexpr int SMEM_BYTES = 2 * A_BYTES + NS * CHUNK + STAGE_BYTES + BIAS_BYTES + PART_BYTES + 256 + 1024;
+#ifndef HMVIT_QKV_PW
+#define HMVIT_QKV_PW 4
+#endif
+  static constexpr int PROD_WARPS = HMVIT_QKV_PW;      // 4: one thread per token row; 8: two threads per row (128 channels each)
+  static constexpr int THREADS = (EPI_WARPS + 2 + PROD_WARPS) * 32;   // epilogue | TMA | MMA | A producers
+  static constexpr int W_TMA = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_PROD0 = EPI_WARPS + 2;
+#ifndef HMVIT_QKV_NB
+#define HMVIT_QKV_NB 4
+#endif
+  static constexpr int NB = HMVIT_QKV_NB;              // TMEM accumulator buffers (128 columns each): MMA runs up to NB - 1 chunks ahead
+  static constexpr uint32_t TMEM_COLS = NB * BN;
+  static_assert(NB == 2 || NB == 4, "accumulator buffers: 2 or 4 (TMEM columns must be a power of two)");
 };
 
 template <bool kLN>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(QkvCfg::THREADS, 1)
 qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, const QkvParams p) {
   using Cfg = QkvCfg;
   extern __shared__ uint8_t smem_raw[];
@@ -67,25 +79,24 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
   uint8_t* sB = sA + 2 * Cfg::A_BYTES;                  // [NS][CHUNK]
   uint8_t* sStage = sB + Cfg::NS * Cfg::CHUNK;          // [4][32][256 B]
   float* sBias = reinterpret_cast<float*>(sStage + Cfg::STAGE_BYTES);   // [2][1280]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGE_BYTES + Cfg::BIAS_BYTES);
+  float2* sPart = reinterpret_cast<float2*>(sStage + Cfg::STAGE_BYTES + Cfg::BIAS_BYTES);   // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGE_BYTES + Cfg::BIAS_BYTES + Cfg::PART_BYTES);
   uint64_t* b_full = bars;                  // [NS]
   uint64_t* b_empty = b_full + Cfg::NS;     // [NS]
-  uint64_t* acc_full = b_empty + Cfg::NS;   // [2]
-  uint64_t* acc_empty = acc_full + 2;       // [2]
-  uint64_t* a_full = acc_empty + 2;         // [2]
+  uint64_t* acc_full = b_empty + Cfg::NS;   // [NB]
+  uint64_t* acc_empty = acc_full + Cfg::NB; // [NB]
+  uint64_t* a_full = acc_empty + Cfg::NB;   // [2]
   uint64_t* a_empty = a_full + 2;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::NS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128);
-      mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1);
-    }
+    for (int s = 0; s < Cfg::NB; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], Cfg::EPI_WARPS * 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], Cfg::PROD_WARPS * 32); mbar_init(&a_empty[s], 1); }
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == Cfg::W_MMA) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
   // biases live in shared memory: a global (L2) load per use stalled the epilogue warps (ncu: long scoreboard)
   for (int e = threadIdx.x; e < 2 * Cfg::N_CHUNKS * Cfg::BN; e += Cfg::THREADS) sBias[e] = __ldg(p.bias + e);
   tc_fence_before();
@@ -118,10 +129,13 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
   // L2 lines at the same time
   const int rot = HMVIT_QKV_ROT ? static_cast<int>(blockIdx.x % Cfg::N_CHUNKS) : 0;
 
-  if (warp < 4) {
+  if (warp < Cfg::EPI_WARPS) {
     // ============================ epilogue ============================
-    const int row = threadIdx.x;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    // One warp per scheduler could not hide its own ALU / TMEM / shared-memory latencies (the kernel ran at the
+    // speed of this instruction stream even with loads, stores and MMAs removed), hence two warps per sub-partition:
+    // warp w owns TMEM lanes 32 (w & 3) .. +31 (= tile rows) and the 64-column half (w >> 2) of every chunk.
+    const int q4 = warp & 3, chh = warp >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     uint8_t* stg = sStage + warp * (32 * 128);
     const size_t rows_total = static_cast<size_t>(p.B) * p.L * p.N;
     uint32_t ci = 0;
@@ -132,53 +146,45 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
       for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
         const int c = (cc + rot) % Cfg::N_CHUNKS;
         if (!((chunk_mask >> c) & 1u)) continue;
-        const uint32_t buf = ci & 1u;
-        mbar_wait(&acc_full[buf], (ci >> 1) & 1u);
+        const uint32_t buf = ci % Cfg::NB;
+        mbar_wait(&acc_full[buf], (ci / Cfg::NB) & 1u);
         tc_fence_after();
         const float* bias = sBias + type * (Cfg::N_CHUNKS * Cfg::BN) + c * Cfg::BN;
-        __nv_bfloat16* obase = p.out_rows + (static_cast<size_t>(c >> 1) * rows_total + static_cast<size_t>(a) * p.N + tok0 + warp * 32) * kC +
-                               (c & 1) * Cfg::BN;
-        // the whole 128-column accumulator row goes to registers in one batch of TMEM loads, so the MMA warp gets
-        // the buffer back before the (longer) convert / stage / store part starts
-        uint32_t r0[32], r1[32], r2[32], r3[32];
-        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN, r0);
-        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + 32, r1);
-        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + 64, r2);
-        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + 96, r3);
+        __nv_bfloat16* obase = p.out_rows + (static_cast<size_t>(c >> 1) * rows_total + static_cast<size_t>(a) * p.N + tok0 + q4 * 32) * kC +
+                               (c & 1) * Cfg::BN + chh * 64;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + chh * 64, r0);
+        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + chh * 64 + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
+        mbar_arrive(&acc_empty[buf]);               // accumulator columns are in registers: the MMA warp may refill the buffer
+        const float* bb = bias + chh * 64;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const float* bb = bias + half * 64;
-#pragma unroll
-          for (int k8 = 0; k8 < 8; ++k8) {
-            const uint32_t* r = half == 0 ? ((k8 < 4) ? (r0 + k8 * 8) : (r1 + (k8 - 4) * 8)) : ((k8 < 4) ? (r2 + k8 * 8) : (r3 + (k8 - 4) * 8));
-            const float4 b0 = *reinterpret_cast<const float4*>(bb + k8 * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bb + k8 * 8 + 4);
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(r[0]) + b0.x, __uint_as_float(r[1]) + b0.y);
-            pk.y = pack_bf16x2(__uint_as_float(r[2]) + b0.z, __uint_as_float(r[3]) + b0.w);
-            pk.z = pack_bf16x2(__uint_as_float(r[4]) + b1.x, __uint_as_float(r[5]) + b1.y);
-            pk.w = pack_bf16x2(__uint_as_float(r[6]) + b1.z, __uint_as_float(r[7]) + b1.w);
-            *reinterpret_cast<uint4*>(stg + lane * 128 + ((k8 ^ (lane & 7)) << 4)) = pk;
-          }
-          __syncwarp();
-          // coalesced stores: 4 rows x 128 B per instruction
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + (lane >> 3), u = lane & 7;
-            const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((u ^ (rr & 7)) << 4));
-            if (!(HMVIT_QKV_DBG & 1) || v.x == 0x12345678u)
-            if (tok0 + warp * 32 + rr < p.N) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * kC + half * 64 + u * 8) = v;
-          }
-          __syncwarp();
+        for (int k8 = 0; k8 < 8; ++k8) {
+          const uint32_t* r = (k8 < 4) ? (r0 + k8 * 8) : (r1 + (k8 - 4) * 8);
+          const float4 b0 = *reinterpret_cast<const float4*>(bb + k8 * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bb + k8 * 8 + 4);
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(r[0]) + b0.x, __uint_as_float(r[1]) + b0.y);
+          pk.y = pack_bf16x2(__uint_as_float(r[2]) + b0.z, __uint_as_float(r[3]) + b0.w);
+          pk.z = pack_bf16x2(__uint_as_float(r[4]) + b1.x, __uint_as_float(r[5]) + b1.y);
+          pk.w = pack_bf16x2(__uint_as_float(r[6]) + b1.z, __uint_as_float(r[7]) + b1.w);
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((k8 ^ (lane & 7)) << 4)) = pk;
         }
+        __syncwarp();
+        // coalesced stores: 4 rows x 128 B per instruction
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + (lane >> 3), u = lane & 7;
+          const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((u ^ (rr & 7)) << 4));
+          if (!(HMVIT_QKV_DBG & 1) || v.x == 0x12345678u)
+          if (tok0 + q4 * 32 + rr < p.N) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * kC + u * 8) = v;
+        }
+        __syncwarp();
         ++ci;
       }
     }
-    (void)row;
-  } else if (warp == 4) {
+  } else if (warp == Cfg::W_TMA) {
     // ============================ TMA producer (weights) ============================
     if (lane == 0) {
       tma_prefetch_desc(&tmap0); tma_prefetch_desc(&tmap1);
@@ -200,7 +206,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == Cfg::W_MMA) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(1u, Cfg::BM, Cfg::BN);
@@ -216,8 +222,8 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
           const int c = (cc + rot) % Cfg::N_CHUNKS;
           if (!((chunk_mask >> c) & 1u)) continue;
-          const uint32_t buf = ci & 1u;
-          mbar_wait(&acc_empty[buf], ((ci >> 1) & 1u) ^ 1u);
+          const uint32_t buf = ci % Cfg::NB;
+          mbar_wait(&acc_empty[buf], ((ci / Cfg::NB) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * Cfg::BN;
           for (int kc = 0; kc < Cfg::NCHA; ++kc, ++it) {
@@ -241,7 +247,11 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
     }
   } else {
     // ============================ A producers: typed LayerNorm ============================
-    const int row = threadIdx.x - 192;           // 0..127
+    // PROD_WARPS == 8: two threads per token row, each owns 128 channels -> twice the loads in flight per SM
+    const int pidx = threadIdx.x - Cfg::W_PROD0 * 32;
+    const int row = pidx & 127, half = pidx >> 7;
+    constexpr int CPT = kC / (Cfg::PROD_WARPS / 4);    // channels per thread: 256 or 128
+    const int c_lo = half * CPT;
     uint32_t ti = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int a, tok0; uint32_t chunk_mask;
@@ -256,15 +266,22 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         if (p.stats_in != nullptr) {
           if (valid) { const float2 st = __ldg(p.stats_in + static_cast<size_t>(a) * p.N + tok); mean = st.x; rstd = st.y; }
         } else {
-          const float s0 = valid ? __ldg(src) : 0.f;
+          const float s0 = valid ? __ldg(src) : 0.f;       // common shift of both halves
           float sum = 0.f, sq = 0.f;
 #pragma unroll 1
-          for (int c0 = 0; c0 < kC; c0 += 64) {
+          for (int c0 = c_lo; c0 < c_lo + CPT; c0 += 64) {
             float xv[64];
 #pragma unroll
             for (int e = 0; e < 64; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
 #pragma unroll
             for (int e = 0; e < 64; ++e) { const float d = xv[e] - s0; sum += d; sq += d * d; }
+          }
+          if constexpr (Cfg::PROD_WARPS == 8) {
+            sPart[half * 128 + row] = make_float2(sum, sq);
+            named_bar_sync(2, Cfg::PROD_WARPS * 32);
+            const float2 o = sPart[(half ^ 1) * 128 + row];
+            sum += o.x; sq += o.y;
+            named_bar_sync(2, Cfg::PROD_WARPS * 32);         // sPart is rewritten by the next tile
           }
           const float md = sum * (1.0f / kC);
           mean = s0 + md;
@@ -278,7 +295,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
       uint8_t* dstA = sA + ab * Cfg::A_BYTES;
       bool waited = false;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kC; c0 += 64) {
+      for (int c0 = c_lo; c0 < c_lo + CPT; c0 += 64) {
         float xv[64];
 #pragma unroll
         for (int e = 0; e < 64; ++e) xv[e] = (valid && !(HMVIT_QKV_DBG & 8)) ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
@@ -314,7 +331,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == Cfg::W_MMA) {
     __syncwarp();
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);

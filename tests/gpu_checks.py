@@ -612,7 +612,7 @@ def check_bwd_wgrad():
         res[name] = rel_l2(dw.cpu(), ref)
         assert float(dw[:, :512].abs().max()) == 0.0 and float(dw[:, 768:].abs().max()) == 0.0
     torch.cuda.synchronize()
-    assert all(v < 2e-3 for v in res.values()), res          # tf32 operands (10-bit mantissa), fp32 accumulate
+    assert all(v < 5e-3 for v in res.values()), res          # operands rounded to bf16 while staged, fp32 accumulate
     return res
 
 
