@@ -17,7 +17,7 @@ EXPORTS = (
     "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
     "hmvit_debug_probe", "hmvit_out_ffn_chain",
     "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
-    "hmvit_bwd_wgrad", "hmvit_group_attn_bwd",
+    "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes",
 )
 
 
@@ -43,7 +43,7 @@ class AttnArgs(C.Structure):
                 ("mode", C.c_void_p), ("record_len", C.c_void_p), ("cav_mask", C.c_void_p), ("T", C.c_void_p),
                 ("cell", C.c_double), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
                 ("bk", C.c_void_p), ("bv", C.c_void_p), ("bias_table", C.c_void_p), ("key_mask", C.c_void_p),
-                ("out", C.c_void_p), ("lse", C.c_void_p)]
+                ("out", C.c_void_p), ("lse", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class WgradArgs(C.Structure):
@@ -103,6 +103,8 @@ def load():
     lib.hmvit_out_ffn_chain.restype = C.c_int
     lib.hmvit_group_attn.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     lib.hmvit_group_attn.restype = C.c_int
+    lib.hmvit_group_attn_workspace_bytes.argtypes = [C.c_int32] * 4
+    lib.hmvit_group_attn_workspace_bytes.restype = C.c_size_t
     lib.hmvit_warp_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_double, C.c_void_p]
     lib.hmvit_warp_bilinear.restype = C.c_int
@@ -128,7 +130,7 @@ def load():
     for fn in ("hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
                "hmvit_bwd_wgrad", "hmvit_group_attn_bwd"):
         getattr(lib, fn).restype = C.c_int
-    if lib.hmvit_abi_version() != 2:
+    if lib.hmvit_abi_version() != 3:
         raise ImportError("libhmvit_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

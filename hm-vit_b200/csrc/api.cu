@@ -4,6 +4,7 @@
 #include "rowgemm.cuh"
 #include "attn.cuh"
 #include "attn_tc.cuh"
+#include "attn_split.cuh"
 #include "attn_bwd.cuh"
 #include "bwd.cuh"
 #include "chain.cuh"
@@ -215,6 +216,18 @@ extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
 // ------------------------------------------------------------------------------------------------
 // attention
 // ------------------------------------------------------------------------------------------------
+// timing aid: 1 = only the warp + compaction pass, 2 = only the dense attention pass (on tiles left by an earlier call)
+static int g_split_phase = 0;
+extern "C" int hmvit_debug_split_phase(int phase) { g_split_phase = phase; return HMVIT_OK; }
+
+extern "C" size_t hmvit_group_attn_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W) {
+  const size_t G = static_cast<size_t>(H / 8) * (W / 8), BL = static_cast<size_t>(B) * L;
+  size_t bytes = 2 * BL * G * L * 2 * kBlobBytes;        // compacted key / value tiles (worst case: every key visible)
+  bytes += (BL * G * 4 + 255) / 256 * 256;               // visible-key counts
+  bytes += (BL * G * L * 64 + 255) / 256 * 256;          // key slots
+  return bytes;
+}
+
 extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a != nullptr, "group_attn: null args");
   HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->H > 0 && a->W > 0, "group_attn: bad shape");
@@ -237,6 +250,8 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
     attr_err = cudaFuncSetAttribute(group_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(group_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dense_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem);
   });
   HMVIT_CHECK_CUDA(attr_err);
   AttnParams p;
@@ -247,6 +262,27 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.lse = a->lse;
   dim3 grid((a->H / 8) * (a->W / 8) * 2, a->B * a->L);      // x: (token group, head group)
+  if (a->workspace != nullptr && legacy) {
+    // split form: warp + compaction pass, then dense attention over the compacted key tiles
+    HMVIT_CHECK_ARG(a->L <= kSplitMaxL, "group_attn: the split form handles at most 8 agents per scene");
+    HMVIT_CHECK_ARG(a->workspace_bytes >= hmvit_group_attn_workspace_bytes(a->B, a->L, a->H, a->W), "group_attn: workspace too small");
+    HMVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "group_attn: workspace must be 256-byte aligned");
+    const size_t G = static_cast<size_t>(a->H / 8) * (a->W / 8), BL = static_cast<size_t>(a->B) * a->L;
+    SplitParams sp;
+    sp.a = p;
+    uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+    const size_t tile_bytes = BL * G * a->L * 2 * kBlobBytes;
+    sp.kc = ws; ws += tile_bytes;
+    sp.vc = ws; ws += tile_bytes;
+    sp.nvis = reinterpret_cast<int*>(ws); ws += (BL * G * 4 + 255) / 256 * 256;
+    sp.slots = ws;
+    dim3 grid_c(static_cast<unsigned>(G), a->B * a->L);
+    if (g_split_phase != 2) warp_compact_kernel<<<grid_c, kCompactThreads, 0, static_cast<cudaStream_t>(stream)>>>(sp);
+    HMVIT_CHECK_CUDA(cudaGetLastError());
+    if (g_split_phase != 1) dense_attn_kernel<<<grid, kDenseThreads, kDenseSmem, static_cast<cudaStream_t>(stream)>>>(sp);
+    HMVIT_CHECK_CUDA(cudaGetLastError());
+    return HMVIT_OK;
+  }
   if (legacy || a->lse != nullptr) group_attn_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(p);
   else group_attn_tc_kernel<<<grid, AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
@@ -332,12 +368,22 @@ extern "C" size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, 
   bytes += align_up(rows * 256 * 2, 1024);       // attention output (bf16 rows)
   bytes += align_up(rows * 256 * 4, 1024);       // FFN hidden (fp32 cm, tf32 values; unfused path and head)
   bytes += align_up(rows * 2 * 4, 1024);         // per-row LayerNorm statistics handed from one stage to the next
+  if (L <= kSplitMaxL) bytes += align_up(hmvit_group_attn_workspace_bytes(B, L, H, W), 1024);   // compacted key / value tiles
   return bytes;
 }
 
-extern "C" int hmvit_fusion_launch_count(int32_t num_iters, int32_t head) { return num_iters * 2 * 3 + (head ? 2 : 0); }
+// HMVIT_ATTN_SPLIT=0 keeps the single-kernel attention inside the whole forward (A/B measurements).
+static bool split_attention() {
+  static bool on = [] { const char* e = getenv("HMVIT_ATTN_SPLIT"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
+
+extern "C" int hmvit_fusion_launch_count(int32_t num_iters, int32_t head) {
+  return num_iters * 2 * (split_attention() ? 4 : 3) + (head ? 2 : 0);
+}
 
 static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream);
+
 
 // Scenes are independent, so the forward can be issued scene chunk by scene chunk through all stages with
 // the same workspace (HMVIT_SCENE_CHUNK=n).  Measured on B200 at config 2: slower than one launch per stage
@@ -390,6 +436,8 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
   float* hid = reinterpret_cast<float*>(ws);
   ws += align_up(rows * 256 * 4, 1024);
   float* stats = reinterpret_cast<float*>(ws);
+  ws += align_up(rows * 2 * 4, 1024);
+  void* attn_ws = (a->L <= kSplitMaxL && split_attention()) ? ws : nullptr;
   bool have_stats = false;                        // stats describe the rows currently in xres
 
   for (int it = 0; it < a->num_iters; ++it) {
@@ -413,6 +461,7 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
       t.mode = a->mode; t.record_len = a->record_len; t.cav_mask = a->cav_mask; t.T = a->T; t.cell = a->cell;
       t.q = qkv; t.k = qkv + rows * 256; t.v = qkv + rows * 256 * 3; t.bk = w.bk; t.bv = w.bv; t.bias_table = w.bias_table;
       t.out = att;
+      t.workspace = attn_ws; t.workspace_bytes = attn_ws ? hmvit_group_attn_workspace_bytes(a->B, a->L, a->H, a->W) : 0;
       rc = hmvit_group_attn(&t, stream); if (rc) return rc;
       if (a->unfused) {
         // output projection + residual

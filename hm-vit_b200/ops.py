@@ -4,6 +4,7 @@ torch is used for device memory and the current stream only; every arithmetic st
 path happens inside libhmvit_b200.so.  All tensors must be CUDA, contiguous.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -68,9 +69,31 @@ def out_ffn_chain(*, B, L, N, mode, record_len, o, resid, out, wa0, wa1, ba, w1_
     return out
 
 
+_ATTN_WS = {}
+
+
+def _attn_workspace(B, L, H, W, device):
+    """Scratch for the split attention (compacted key / value tiles), cached per shape and device."""
+    key = (B, L, H, W, str(device))
+    ws = _ATTN_WS.get(key)
+    if ws is None:
+        _ATTN_WS.clear()
+        nbytes = int(_lib.load().hmvit_group_attn_workspace_bytes(B, L, H, W))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ATTN_WS[key] = ws
+    return ws
+
+
 def group_attn(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, k, v, bk, bv, bias_table, out,
-               ego_only=False, key_mask=None, lse=None):
+               ego_only=False, key_mask=None, lse=None, split=None):
+    """split=None: the split form (warp + compaction pass, dense attention pass) whenever L <= 8 unless
+    HMVIT_ATTN_SPLIT=0; split=False: the single fused kernel."""
     args = _lib.AttnArgs()
+    if split is None:
+        split = L <= 8 and os.environ.get("HMVIT_ATTN_SPLIT", "1") != "0"
+    if split:
+        ws = _attn_workspace(B, L, H, W, q.device)
+        args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
     args.B, args.L, args.H, args.W = B, L, H, W
     args.kind = kind
     args.ego_only = 1 if ego_only else 0

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMVIT_ABI_VERSION 2
+#define HMVIT_ABI_VERSION 3
 
 /* error codes */
 #define HMVIT_OK 0
@@ -136,9 +136,15 @@ typedef struct {
   void* out;                  /* bf16 rows [B*L*N][256] */
   float* lse;                 /* optional [B*L*N][8]: log2-domain log-sum-exp per (query token, head), saved for
                                  hmvit_group_attn_bwd; NULL = not written (inference) */
+  void* workspace;            /* optional scratch of >= hmvit_group_attn_workspace_bytes(B, L, H, W) bytes (256-byte
+                                 aligned).  Non-NULL selects the split form: a warp + compaction pass writes the
+                                 visible, blended keys / values of every (ego, group) as dense 64-key tiles, then a
+                                 dense attention pass consumes them (csrc/attn_split.cuh).  NULL: single kernel. */
+  size_t workspace_bytes;
 } HmvitAttnArgs;
 
 int hmvit_group_attn(const HmvitAttnArgs* args, void* stream);
+size_t hmvit_group_attn_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W);
 
 /* ---- stand-alone spatial warp and ROI mask (unit-parity surface) ------------------------------------
  * SpatialTransformation.forward  opencood/models/sub_modules/spatial_transformation.py:16-44

@@ -522,6 +522,7 @@ def check_ragged_batch():
 
 
 CHECKS.update({"cuda_graph": check_cuda_graph, "ragged_batch": check_ragged_batch})
+# (attn_split_vs_single is registered next to the backward checks below: it uses tests/emul_ops.py)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -701,6 +702,52 @@ def check_attn_bwd():
     return res
 
 
+def check_attn_split_vs_single():
+    """The split attention (warp + compaction pass, dense attention pass) against the emulated attention and against the
+    single fused kernel: 7 agents (two tap passes in the single kernel), ragged record_len, window / grid / ego-only,
+    softmax statistics; plus a NON-identity diagonal transform (the ego's own keys then take the general warp path)."""
+    res = {}
+    for kind, ego_only, seed, twist in ((0, False, 41, False), (1, False, 42, False), (1, True, 43, False), (1, False, 44, True)):
+        p = pkg()
+        ops = p.ops
+        g = _geo_small(seed=seed, B=2, L=7, H=16, W=24, record_len=(7, 4))
+        if twist:
+            g["T"][0, 1, 1] = g["T"][0, 2, 1].clone()          # slot 1 of scene 0 warps its own features
+        B, L, H, W, N = g["B"], g["L"], g["H"], g["W"], g["N"]
+        R = B * L * N
+        gen = torch.Generator().manual_seed(seed)
+        q = (torch.randn(R, 256, generator=gen) * 0.6).to(torch.bfloat16)
+        k = (torch.randn(2, R, 256, generator=gen) * 0.6).to(torch.bfloat16)
+        v = torch.randn(2, R, 256, generator=gen).to(torch.bfloat16)
+        bk, bv = torch.randn(2, 2, 256, generator=gen) * 0.1, torch.randn(2, 2, 256, generator=gen) * 0.1
+        table = torch.randn(225, 8, generator=gen)
+        geo = dict(B=B, L=L, H=H, W=W, kind=kind, cell=1.6, ego_only=ego_only)
+        cpu = dict(mode=g["mode"], record_len=g["rl"], cav_mask=g["cav"], T=g["T"])
+        dev = {kk: vv.to(DEV).contiguous() for kk, vv in cpu.items()}
+        outs, lses = {}, {}
+        for split in (True, False):
+            outs[split] = torch.zeros(R, 256, dtype=torch.bfloat16, device=DEV)
+            lses[split] = torch.zeros(R, 8, device=DEV)
+            ops.group_attn(q=q.to(DEV), k=k.to(DEV), v=v.to(DEV), bk=bk.to(DEV), bv=bv.to(DEV), bias_table=table.to(DEV),
+                           out=outs[split], lse=lses[split], split=split, **geo, **dev)
+        out_ref, lse_ref = torch.zeros(R, 256), torch.zeros(R, 8)
+        EM.group_attn(q=q.float(), k=k.float(), v=v.float(), bk=bk, bv=bv, bias_table=table, out=out_ref, lse=lse_ref, **geo, **cpu)
+        tag = f"kind{kind}_ego{int(ego_only)}" + ("_twist" if twist else "")
+        # a query that sees no key at all (possible only with the twisted diagonal) is NaN in the emulation (softmax of an
+        # empty set) and 0 in the kernels: compare the rows that have keys
+        ok = torch.isfinite(out_ref).all(-1)
+        res[f"split_{tag}"] = rel_l2(outs[True].float().cpu()[ok], out_ref[ok])
+        res[f"single_{tag}"] = rel_l2(outs[False].float().cpu()[ok], out_ref[ok])
+        assert float(outs[True].float().cpu()[~ok].abs().sum()) == 0.0, tag
+        fin = torch.isfinite(lse_ref)
+        assert bool((torch.isfinite(lses[True].cpu()) == fin).all()), tag
+        res[f"lse_abs_{tag}"] = float((lses[True].cpu()[fin] - lse_ref[fin]).abs().max())
+    torch.cuda.synchronize()
+    for n, val in res.items():
+        assert val < (0.03 if n.startswith("lse_abs") else 2e-2), (n, val, res)
+    return res
+
+
 def _train_case(B, L, H, W, record_len, seed, mode=None, skip_dead=True):
     cfg = O.default_config()
     cfg["hetero_fusion_block"]["drop_out"] = 0.0
@@ -793,4 +840,5 @@ def check_train_api():
 
 CHECKS.update({"bwd_small_kernels": check_bwd_small_kernels, "bwd_wgrad": check_bwd_wgrad,
                "bwd_lin_variants": check_bwd_lin_variants, "attn_bwd": check_attn_bwd,
-               "train_grads_small": check_train_grads_small, "train_api": check_train_api})
+               "train_grads_small": check_train_grads_small, "train_api": check_train_api,
+               "attn_split_vs_single": check_attn_split_vs_single})

@@ -13,6 +13,31 @@ def test_gpu_check(name):
     print(name, res)
 
 
+def _run_with_env(name, **env_extra):
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **env_extra)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "bringup.py"), "--one", name], capture_output=True,
+                       text=True, env=env, timeout=600)
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert line, r.stdout[-500:] + r.stderr[-500:]
+    res = json.loads(line[-1])
+    assert res["status"] == "ok", res
+
+
+SINGLE_CHECKS = ["attention_golden", "fusion_golden", "ragged_batch", "fusion_properties"]
+
+
+@pytest.mark.parametrize("name", SINGLE_CHECKS)
+def test_gpu_check_single_kernel_attention(name):
+    """The default attention is the split form (csrc/attn_split.cuh); HMVIT_ATTN_SPLIT=0 selects the single fused
+    warp + mask + attention kernel (csrc/attn.cuh), which stays parity-tested.  The switch is read once per process."""
+    _run_with_env(name, HMVIT_ATTN_SPLIT="0")
+
+
 TC_CHECKS = ["attention_golden", "fusion_golden", "fusion_config2_scene", "ragged_batch", "fusion_properties"]
 
 
