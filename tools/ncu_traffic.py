@@ -28,8 +28,7 @@ def main():
     res = {k: {"dram_bytes_per_launch": v["bytes"] / v["launches"], "launches_profiled": v["launches"],
                "profiled_duration_" + units[it]: v["dur"] / v["launches"]} for k, v in acc.items()}
     res["_source"] = {"report": os.path.basename(rep),
-                      "command": "ncu --set full --clock-control none --import-source on -k regex:\"group_attn_kernel|qkv_kernel|chain_kernel\" "
-                                 "-s 15 -c 3 python bench.py --steps 1 --warmup 3 --no-cpu-baseline"}
+                      "command": sys.argv[2] if len(sys.argv) > 2 else "ncu --set full --clock-control none --import-source on ... python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-train"}
     json.dump(res, open(os.path.join(ROOT, "profiles", "r1_traffic.json"), "w"), indent=1)
     print(json.dumps(res, indent=1))
 
