@@ -660,6 +660,10 @@ extern "C" int hmvit_debug_tc_ts(unsigned long long* host_out /* [8][3][64] */) 
   HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_tc_ts, sizeof(unsigned long long) * 8 * 3 * 64));
   return HMVIT_OK;
 }
+extern "C" int hmvit_debug_qkv_ts(unsigned long long* host_out /* [3][512] */) {
+  HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_qkv_ts, sizeof(unsigned long long) * 3 * 512));
+  return HMVIT_OK;
+}
 extern "C" int hmvit_debug_chain_ts(unsigned long long* host_out /* [2][16][16] */) {
   HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_chain_ts, sizeof(unsigned long long) * 2 * 16 * 16));
   return HMVIT_OK;

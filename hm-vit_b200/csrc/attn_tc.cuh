@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(AttnTcCfg::THREADS, 2) group_attn_tc_kernel(co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sK = smem + Cfg::OFF_K;
   uint8_t* sV = smem + Cfg::OFF_V;

@@ -86,7 +86,7 @@ HMVIT_DEVINL float2 ln_combine(const float2* part, int row, float eps) {
 __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   using Cfg = ChainCfg;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sO = smem;
   uint8_t* sF = smem + Cfg::AO_BYTES;
   uint8_t* sW = sF + Cfg::NF * Cfg::CHUNK;

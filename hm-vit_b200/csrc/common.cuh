@@ -23,6 +23,15 @@ constexpr int kS = 64;         // tokens per group (window^2)
 // ------------------------------------------------------------------------------------------
 HMVIT_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// 1024-byte aligned start of the dynamic shared memory.  The pad is computed on the 32-bit shared-window
+// address and ADDED to the __shared__ array, so the compiler keeps the pointer in the shared address space
+// (LDS / STS).  Rounding a uintptr_t and casting back yields a generic pointer: every shared access then
+// compiles to a generic LD / ST through the global-memory path (seen in SASS as LD.E / ST.E + long scoreboard).
+HMVIT_DEVINL uint8_t* smem_align1024(uint8_t* smem_raw) {
+  const uint32_t base = smem_u32(smem_raw);
+  return smem_raw + (((base + 1023u) & ~1023u) - base);
+}
+
 HMVIT_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);

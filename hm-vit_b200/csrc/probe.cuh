@@ -11,7 +11,7 @@ __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D,
                   int N, int b_mn_major /* bit 0: B MN-major, bit 1: A operand from TMEM */, uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;              // 128 rows x 128 B
   uint8_t* sB = smem + 16384;      // up to 128 rows x 128 B (K-major) / 2 MN blocks of 64 rows x 128 B
   __shared__ uint64_t bar;

@@ -20,6 +20,13 @@
 
 namespace hmvit {
 
+#ifdef HMVIT_TS   // timeline instrumentation build: CTA 0 records clock64() per role (tools/qkv_timeline.py)
+__device__ unsigned long long g_qkv_ts[3][512];   // [role: 0 epilogue warp 0, 1 MMA issuer, 2 producer warp 0][event]
+#define QKV_TS(role, idx) do { if (blockIdx.x == 0 && (idx) < 512) g_qkv_ts[role][idx] = clock64(); } while (0)
+#else
+#define QKV_TS(role, idx) do { } while (0)
+#endif
+
 struct QkvParams {
   int B, L, N;
   const int* mode;             // [B*L]
@@ -74,7 +81,7 @@ __global__ void __launch_bounds__(QkvCfg::THREADS, 1)
 qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, const QkvParams p) {
   using Cfg = QkvCfg;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;                                   // [2][A_BYTES]
   uint8_t* sB = sA + 2 * Cfg::A_BYTES;                  // [NS][CHUNK]
   uint8_t* sStage = sB + Cfg::NS * Cfg::CHUNK;          // [4][32][256 B]
@@ -147,8 +154,10 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         const int c = (cc + rot) % Cfg::N_CHUNKS;
         if (!((chunk_mask >> c) & 1u)) continue;
         const uint32_t buf = ci % Cfg::NB;
+        if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 0);
         mbar_wait(&acc_full[buf], (ci / Cfg::NB) & 1u);
         tc_fence_after();
+        if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 1);
         const float* bias = sBias + type * (Cfg::N_CHUNKS * Cfg::BN) + c * Cfg::BN;
         __nv_bfloat16* obase = p.out_rows + (static_cast<size_t>(c >> 1) * rows_total + static_cast<size_t>(a) * p.N + tok0 + q4 * 32) * kC +
                                (c & 1) * Cfg::BN + chh * 64;
@@ -158,6 +167,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&acc_empty[buf]);               // accumulator columns are in registers: the MMA warp may refill the buffer
+        if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 2);
         const float* bb = bias + chh * 64;
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8) {
@@ -172,6 +182,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
           *reinterpret_cast<uint4*>(stg + lane * 128 + ((k8 ^ (lane & 7)) << 4)) = pk;
         }
         __syncwarp();
+        if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 3);
         // coalesced stores: 4 rows x 128 B per instruction
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
@@ -181,6 +192,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
           if (tok0 + q4 * 32 + rr < p.N) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * kC + u * 8) = v;
         }
         __syncwarp();
+        if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 4);
         ++ci;
       }
     }
@@ -223,8 +235,10 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
           const int c = (cc + rot) % Cfg::N_CHUNKS;
           if (!((chunk_mask >> c) & 1u)) continue;
           const uint32_t buf = ci % Cfg::NB;
+          QKV_TS(1, ci * 3 + 0);
           mbar_wait(&acc_empty[buf], ((ci / Cfg::NB) & 1u) ^ 1u);
           tc_fence_after();
+          QKV_TS(1, ci * 3 + 1);
           const uint32_t d_tmem = tmem_base + buf * Cfg::BN;
           for (int kc = 0; kc < Cfg::NCHA; ++kc, ++it) {
             const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
@@ -239,6 +253,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
             umma_commit(&b_empty[s]);
           }
           umma_commit(&acc_full[buf]);
+          QKV_TS(1, ci * 3 + 2);
           ++ci;
         }
         umma_commit(&a_empty[ab]);               // every MMA that reads this A buffer has retired
@@ -258,6 +273,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
       if (!tile_info(t, a, tok0, chunk_mask)) continue;
       const int type = p.mode[a] != 0 ? 1 : 0;
       const uint32_t ab = ti & 1u;
+      if (pidx == 0) QKV_TS(2, ti * 4 + 0);
       const int tok = tok0 + row;
       const bool valid = tok < p.N;
       const float* src = p.x_cm + static_cast<size_t>(a) * kC * p.N + (valid ? tok : 0);
@@ -312,7 +328,11 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
             for (int e = 0; e < 64; ++e) xv[e] = 0.f;
           }
         }
-        if (!waited) { mbar_wait(&a_empty[ab], ((ti >> 1) & 1u) ^ 1u); waited = true; }   // loads above overlap the wait
+        if (!waited) {
+          if (pidx == 0) QKV_TS(2, ti * 4 + 1);
+          mbar_wait(&a_empty[ab], ((ti >> 1) & 1u) ^ 1u); waited = true;   // loads above overlap the wait
+          if (pidx == 0) QKV_TS(2, ti * 4 + 2);
+        }
 #pragma unroll
         for (int uu = 0; uu < 8; ++uu) {
           const float* v = xv + uu * 8;
@@ -325,6 +345,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
       }
       fence_proxy_async_smem();
       mbar_arrive(&a_full[ab]);
+      if (pidx == 0) QKV_TS(2, ti * 4 + 3);
       ++ti;
     }
   }

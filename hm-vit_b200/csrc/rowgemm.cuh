@@ -91,7 +91,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
   }
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::A_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::A_BYTES + Cfg::B_BYTES);
