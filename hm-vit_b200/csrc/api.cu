@@ -77,6 +77,7 @@ static int num_sms() {
 
 template <bool kLN>
 static int launch_qkv(const CUtensorMap& m0, const CUtensorMap& m1, const QkvParams& p, cudaStream_t st) {
+
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {

@@ -63,15 +63,6 @@ HMVIT_DEVINL void tmem_st1(uint32_t taddr, uint32_t r) {
 }
 // MN-major operand (rows of 128 B = 64 consecutive MN elements for one k; 8-row groups 1024 B apart)
 HMVIT_DEVINL uint64_t umma_desc_sw128_mn(uint32_t smem_addr) { return umma_desc_sw128(smem_addr); }
-// D[tmem] (+)= A[tmem] * B[smem]^T, bf16 (A: one row per lane, two K elements per 32-bit column)
-HMVIT_DEVINL void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
 // folded key / value biases of the pass's sources for this head group, as bf16 rows in shared memory
 HMVIT_DEVINL void stage_kv_bias(const AttnParams& p, uint8_t* sKvb, int b, int j0, int nsrc, int te, int hgc, int t, int nt) {
   for (int e = t; e < nsrc * 2 * 64; e += nt) {              // one bf16 pair per element

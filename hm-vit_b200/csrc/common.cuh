@@ -108,6 +108,34 @@ HMVIT_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// one lane of a CONVERGED warp (elect.sync): the warp keeps executing uniformly around a single-thread instruction,
+// so the compiler can hold descriptors / addresses in uniform registers (an `if (lane == 0)` region makes every
+// operand of a tcgen05.mma go through a per-instruction R2UR loop: ~100 issue cycles per MMA, measured)
+HMVIT_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// volatile shared-memory accesses: keep a hand-scheduled batch of loads / stores in program order
+HMVIT_DEVINL float4 lds_f4(const void* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+HMVIT_DEVINL uint4 lds_u4(const void* p) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+HMVIT_DEVINL void sts_u4(void* p, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // make generic-proxy smem writes visible to the async proxy (TMA / UMMA operand reads)
 HMVIT_DEVINL void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -123,6 +151,15 @@ HMVIT_DEVINL void tma_load_2d(void* smem_dst, const void* tmap, uint64_t* bar, i
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+
+// TMA 3-D tiled store (shared -> global, bulk async group of the issuing thread); out-of-range box rows are clipped
+HMVIT_DEVINL void tma_store_3d(const void* tmap, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+HMVIT_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kN> HMVIT_DEVINL void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kN) : "memory"); }
+template <int kN> HMVIT_DEVINL void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kN) : "memory"); }
 
 // ------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, UMMA, commit, TMEM <-> registers
@@ -174,6 +211,15 @@ HMVIT_DEVINL void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uin
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, bf16 (A: one row per TMEM lane, two K elements per 32-bit column, 8 columns
+// per K = 16 instruction).  The A operand never crosses the shared-memory port.
+HMVIT_DEVINL void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // arrive on an mbarrier when all previously issued UMMAs of this thread have completed
 HMVIT_DEVINL void umma_commit(uint64_t* bar) {

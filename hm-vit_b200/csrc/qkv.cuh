@@ -6,12 +6,18 @@
 // (hetero_fusion.py:111-140) + get_hetero_edge_weights (:154-185; relation_att / relation_msg are
 // folded into W_k / W_v on the host) for every valid agent of every scene in one launch.
 //
-// One CTA per SM loops over 128-token tiles.  Warp roles (14 warps; numbering in QkvCfg):
-//   4 warps    A producers: typed LayerNorm of the NEXT tile (channel-major fp32 -> bf16, UMMA
-//              SWIZZLE_128B layout) into one of two A buffers, overlapped with the current tile's MMAs
-//   1 warp     TMA producer: weight stages (128 output channels x 128 B of K), 3-deep ring
-//   1 warp     MMA issuer: 16 x tcgen05.mma (M128 N128 K16) per 128-column chunk, 2 TMEM buffers
-//   warps 0-7  epilogue: TMEM -> +bias -> bf16 -> swizzled smem staging -> fully coalesced row stores
+// One CTA per SM loops over 128-token tiles.  Warp roles (18 warps; numbering in QkvCfg):
+//   8 warps    A producers: typed LayerNorm of the NEXT tile (channel-major fp32 -> packed bf16) written with
+//              tcgen05.st into one of two A buffers IN TENSOR MEMORY (thread == token row == TMEM lane, two
+//              warps per lane quarter, 128 channels each), overlapped with the current tile's MMAs.  The A
+//              operand never touches shared memory: with A in smem every M128 N128 K16 MMA read 8 KB per
+//              64 cycles = the whole 128 B/clk shared-memory port, which starved the epilogue's staging
+//              (measured: 1.4-2.0 k cycles for 130 instructions; tools/qkv_timeline.py)
+//   1 warp     TMA producer: weight stages (128 output channels x 128 B of K), NS-deep ring
+//   1 warp     MMA issuer: 16 x tcgen05.mma (A from TMEM, M128 N128 K16) per 128-column chunk, 2 accumulators
+//   warps 0-7  epilogue: TMEM -> +bias -> bf16 -> swizzled smem staging -> fully coalesced row stores (a TMA tensor
+//              store from the staging tile was measured slower: 4 KB boxes queue behind the weight loads in the
+//              SM's TMA unit, the staging buffer stayed busy for ~3 k cycles)
 // Only the chunks a scene needs are computed (K'/V' for the ego types present; in the last stage Q
 // for slot 0 only).
 #pragma once
@@ -44,36 +50,40 @@ struct QkvParams {
 struct QkvCfg {
   static constexpr int BM = 128, BN = 128;
   static constexpr int CHUNK = 16384;
-  static constexpr int NCHA = 4;                       // A chunks (bf16, K = 256)
+  static constexpr int NCHA = 4;                       // K chunks of 64 channels (one weight stage each)
 #ifndef HMVIT_QKV_NS
-#define HMVIT_QKV_NS 3
+#define HMVIT_QKV_NS 2
+#endif
+#ifndef HMVIT_QKV_SUB      // 64-channel K chunks per weight stage: a successful mbarrier wait costs the single MMA-issuing
+#define HMVIT_QKV_SUB 4    // thread 200-300 cycles (tools/qkv_timeline.py), so stages are made large and waits few
 #endif
 #ifndef HMVIT_QKV_ROT
-#define HMVIT_QKV_ROT 1
+#define HMVIT_QKV_ROT 0
 #endif
 #ifndef HMVIT_QKV_DBG      // bottleneck-hunting builds only (results are wrong): 1 no stores, 2 no weight TMA, 4 no MMA, 8 no x loads
 #define HMVIT_QKV_DBG 0
 #endif
   static constexpr int NS = HMVIT_QKV_NS;              // weight ring stages
+  static constexpr int SUB = HMVIT_QKV_SUB;            // K chunks per stage
+  static constexpr int STAGE = SUB * CHUNK;            // bytes per weight stage
+  static_assert(NCHA % SUB == 0, "stage size");
   static constexpr int N_CHUNKS = 10;                  // 1280 / 128
-  static constexpr int A_BYTES = NCHA * CHUNK;         // 64 KB per A buffer
+  static constexpr uint32_t A_COLS = kC / 2;           // TMEM columns per A buffer: 128 lanes x 256 bf16, two per column
   static constexpr int EPI_WARPS = 8;                  // 2 per SM sub-partition: (TMEM lane quarter, 64-column half of the chunk)
   static constexpr int STAGE_BYTES = EPI_WARPS * 32 * 128;   // epilogue staging: per warp 32 rows x 128 B (64 columns)
   static constexpr int BIAS_BYTES = 2 * N_CHUNKS * BN * 4; // both types' [1280] biases, read by every epilogue thread
   static constexpr int PART_BYTES = 2 * 128 * 8;       // partial LayerNorm sums exchanged between the two threads of a row
-  static constexpr int SMEM_BYTES = 2 * A_BYTES + NS * CHUNK + STAGE_BYTES + BIAS_BYTES + PART_BYTES + 256 + 1024;
+  static constexpr int SMEM_BYTES = NS * STAGE + STAGE_BYTES + BIAS_BYTES + PART_BYTES + 256 + 1024;
 #ifndef HMVIT_QKV_PW
-#define HMVIT_QKV_PW 4
+#define HMVIT_QKV_PW 8
 #endif
   static constexpr int PROD_WARPS = HMVIT_QKV_PW;      // 4: one thread per token row; 8: two threads per row (128 channels each)
   static constexpr int THREADS = (EPI_WARPS + 2 + PROD_WARPS) * 32;   // epilogue | TMA | MMA | A producers
   static constexpr int W_TMA = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_PROD0 = EPI_WARPS + 2;
-#ifndef HMVIT_QKV_NB
-#define HMVIT_QKV_NB 4
-#endif
-  static constexpr int NB = HMVIT_QKV_NB;              // TMEM accumulator buffers (128 columns each): MMA runs up to NB - 1 chunks ahead
-  static constexpr uint32_t TMEM_COLS = NB * BN;
-  static_assert(NB == 2 || NB == 4, "accumulator buffers: 2 or 4 (TMEM columns must be a power of two)");
+  static constexpr int NB = 2;                         // TMEM accumulator buffers (128 columns each): MMA runs one chunk ahead
+  static constexpr uint32_t TM_ACC = 2 * A_COLS;       // columns: A buffer 0 | A buffer 1 | accumulator 0 | accumulator 1
+  static constexpr uint32_t TMEM_COLS = TM_ACC + NB * BN;
+  static_assert(TMEM_COLS == 512, "TMEM budget");
 };
 
 template <bool kLN>
@@ -82,9 +92,8 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
   using Cfg = QkvCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
-  uint8_t* sA = smem;                                   // [2][A_BYTES]
-  uint8_t* sB = sA + 2 * Cfg::A_BYTES;                  // [NS][CHUNK]
-  uint8_t* sStage = sB + Cfg::NS * Cfg::CHUNK;          // [4][32][256 B]
+  uint8_t* sB = smem;                                   // [NS][CHUNK]
+  uint8_t* sStage = sB + Cfg::NS * Cfg::STAGE;          // [8 warps][32 rows][128 B]
   float* sBias = reinterpret_cast<float*>(sStage + Cfg::STAGE_BYTES);   // [2][1280]
   float2* sPart = reinterpret_cast<float2*>(sStage + Cfg::STAGE_BYTES + Cfg::BIAS_BYTES);   // [2][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sStage + Cfg::STAGE_BYTES + Cfg::BIAS_BYTES + Cfg::PART_BYTES);
@@ -154,21 +163,20 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         const int c = (cc + rot) % Cfg::N_CHUNKS;
         if (!((chunk_mask >> c) & 1u)) continue;
         const uint32_t buf = ci % Cfg::NB;
+        const float* bb = sBias + type * (Cfg::N_CHUNKS * Cfg::BN) + c * Cfg::BN + chh * 64;
+        __nv_bfloat16* obase = p.out_rows + (static_cast<size_t>(c >> 1) * rows_total + static_cast<size_t>(a) * p.N + tok0 + q4 * 32) * kC +
+                               (c & 1) * Cfg::BN + chh * 64;
         if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 0);
         mbar_wait(&acc_full[buf], (ci / Cfg::NB) & 1u);
         tc_fence_after();
         if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 1);
-        const float* bias = sBias + type * (Cfg::N_CHUNKS * Cfg::BN) + c * Cfg::BN;
-        __nv_bfloat16* obase = p.out_rows + (static_cast<size_t>(c >> 1) * rows_total + static_cast<size_t>(a) * p.N + tok0 + q4 * 32) * kC +
-                               (c & 1) * Cfg::BN + chh * 64;
         uint32_t r0[32], r1[32];
-        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + chh * 64, r0);
-        tmem_ld32(tmem_base + lane_base + buf * Cfg::BN + chh * 64 + 32, r1);
+        tmem_ld32(tmem_base + lane_base + Cfg::TM_ACC + buf * Cfg::BN + chh * 64, r0);
+        tmem_ld32(tmem_base + lane_base + Cfg::TM_ACC + buf * Cfg::BN + chh * 64 + 32, r1);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&acc_empty[buf]);               // accumulator columns are in registers: the MMA warp may refill the buffer
         if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 2);
-        const float* bb = bias + chh * 64;
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8) {
           const uint32_t* r = (k8 < 4) ? (r0 + k8 * 8) : (r1 + (k8 - 4) * 8);
@@ -208,21 +216,25 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
           const int c = (cc + rot) % Cfg::N_CHUNKS;
           if (!((chunk_mask >> c) & 1u)) continue;
-          for (int kc = 0; kc < Cfg::NCHA; ++kc, ++it) {
+          for (int kc = 0; kc < Cfg::NCHA; kc += Cfg::SUB, ++it) {
             const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
             mbar_wait(&b_empty[s], ph ^ 1u);
             if ((HMVIT_QKV_DBG & 2) && it >= Cfg::NS) { mbar_arrive(&b_full[s]); continue; }
-            mbar_arrive_expect_tx(&b_full[s], Cfg::CHUNK);
-            tma_load_2d(sB + s * Cfg::CHUNK, tmap, &b_full[s], kc * 64, c * Cfg::BN);
+            mbar_arrive_expect_tx(&b_full[s], Cfg::STAGE);
+#pragma unroll
+            for (int j = 0; j < Cfg::SUB; ++j)
+              tma_load_2d(sB + s * Cfg::STAGE + j * Cfg::CHUNK, tmap, &b_full[s], (kc + j) * 64, c * Cfg::BN);
           }
         }
       }
     }
   } else if (warp == Cfg::W_MMA) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // The whole warp runs the loop (uniform control flow); one elected lane issues the MMAs and commits.
+    {
       constexpr uint32_t idesc = umma_idesc(1u, Cfg::BM, Cfg::BN);
-      const uint32_t a_base0 = smem_u32(sA), b_base = smem_u32(sB);
+      const uint32_t b_base = smem_u32(sB);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t it = 0, ci = 0, ti = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int a, tok0; uint32_t chunk_mask;
@@ -230,41 +242,49 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         const uint32_t ab = ti & 1u;
         mbar_wait(&a_full[ab], (ti >> 1) & 1u);
         tc_fence_after();
-        const uint32_t a_base = a_base0 + ab * Cfg::A_BYTES;
+        const uint32_t a_tmem = tm + ab * Cfg::A_COLS;
         for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
           const int c = (cc + rot) % Cfg::N_CHUNKS;
           if (!((chunk_mask >> c) & 1u)) continue;
           const uint32_t buf = ci % Cfg::NB;
-          QKV_TS(1, ci * 3 + 0);
+          if (lane == 0) QKV_TS(1, ci * 3 + 0);
           mbar_wait(&acc_empty[buf], ((ci / Cfg::NB) & 1u) ^ 1u);
           tc_fence_after();
-          QKV_TS(1, ci * 3 + 1);
-          const uint32_t d_tmem = tmem_base + buf * Cfg::BN;
-          for (int kc = 0; kc < Cfg::NCHA; ++kc, ++it) {
+          if (lane == 0) QKV_TS(1, ci * 3 + 1);
+          const uint32_t d_tmem = tm + Cfg::TM_ACC + buf * Cfg::BN;
+          for (int kc = 0; kc < Cfg::NCHA; kc += Cfg::SUB, ++it) {
             const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
             mbar_wait(&b_full[s], ph);
             tc_fence_after();
-            if (!(HMVIT_QKV_DBG & 4)) {
+            if (elect_one()) {
+              if (!(HMVIT_QKV_DBG & 4)) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                umma_ss<2>(d_tmem, umma_desc_sw128(a_base + kc * Cfg::CHUNK + ks * 32),
-                           umma_desc_sw128(b_base + s * Cfg::CHUNK + ks * 32), idesc, (kc | ks) != 0 ? 1u : 0u);
+                for (int j = 0; j < Cfg::SUB; ++j)
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_ts_bf16(d_tmem, a_tmem + (kc + j) * 32 + ks * 8,
+                                 umma_desc_sw128(b_base + s * Cfg::STAGE + j * Cfg::CHUNK + ks * 32), idesc, (kc | j | ks) != 0 ? 1u : 0u);
+              }
+              umma_commit(&b_empty[s]);
+              if (kc + Cfg::SUB >= Cfg::NCHA) umma_commit(&acc_full[buf]);
             }
-            umma_commit(&b_empty[s]);
+            __syncwarp();
           }
-          umma_commit(&acc_full[buf]);
-          QKV_TS(1, ci * 3 + 2);
+          if (lane == 0) QKV_TS(1, ci * 3 + 2);
           ++ci;
         }
-        umma_commit(&a_empty[ab]);               // every MMA that reads this A buffer has retired
+        if (elect_one()) umma_commit(&a_empty[ab]);               // every MMA that reads this A buffer has retired
+        __syncwarp();
         ++ti;
       }
     }
   } else {
     // ============================ A producers: typed LayerNorm ============================
-    // PROD_WARPS == 8: two threads per token row, each owns 128 channels -> twice the loads in flight per SM
+    // PROD_WARPS == 8: two threads per token row, each owns 128 channels -> twice the loads in flight per SM.
+    // A warp can only touch the TMEM lane quarter (warp % 4), which fixes the rows it produces.
     const int pidx = threadIdx.x - Cfg::W_PROD0 * 32;
-    const int row = pidx & 127, half = pidx >> 7;
+    const int row = (warp & 3) * 32 + lane, half = (warp - Cfg::W_PROD0) >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     constexpr int CPT = kC / (Cfg::PROD_WARPS / 4);    // channels per thread: 256 or 128
     const int c_lo = half * CPT;
     uint32_t ti = 0;
@@ -308,7 +328,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
       const float* gam = affine ? p.ln_gamma + type * kC : nullptr;
       const float* bet = affine ? p.ln_beta + type * kC : nullptr;
       const float nmr = -mean * rstd;
-      uint8_t* dstA = sA + ab * Cfg::A_BYTES;
+      const uint32_t dstA = tmem_base + lane_base + ab * Cfg::A_COLS;
       bool waited = false;
 #pragma unroll 1
       for (int c0 = c_lo; c0 < c_lo + CPT; c0 += 64) {
@@ -331,19 +351,16 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         if (!waited) {
           if (pidx == 0) QKV_TS(2, ti * 4 + 1);
           mbar_wait(&a_empty[ab], ((ti >> 1) & 1u) ^ 1u); waited = true;   // loads above overlap the wait
+          tc_fence_after();
           if (pidx == 0) QKV_TS(2, ti * 4 + 2);
         }
+        uint32_t pk[32];
 #pragma unroll
-        for (int uu = 0; uu < 8; ++uu) {
-          const float* v = xv + uu * 8;
-          const int u = c0 / 8 + uu;
-          uint4 pk;
-          pk.x = pack_bf16x2(v[0], v[1]); pk.y = pack_bf16x2(v[2], v[3]);
-          pk.z = pack_bf16x2(v[4], v[5]); pk.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(dstA + (u >> 3) * Cfg::CHUNK + sw128_offset(row, u & 7)) = pk;
-        }
+        for (int e = 0; e < 32; ++e) pk[e] = pack_bf16x2(xv[2 * e], xv[2 * e + 1]);
+        tmem_st32(dstA + c0 / 2, pk);
       }
-      fence_proxy_async_smem();
+      tmem_st_wait();
+      tc_fence_before();
       mbar_arrive(&a_full[ab]);
       if (pidx == 0) QKV_TS(2, ti * 4 + 3);
       ++ti;
