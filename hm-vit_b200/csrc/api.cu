@@ -5,6 +5,7 @@
 #include "attn.cuh"
 #include "attn_tc.cuh"
 #include "attn_split.cuh"
+#include "attn_dense_tc.cuh"
 #include "attn_bwd.cuh"
 #include "bwd.cuh"
 #include "chain.cuh"
@@ -217,6 +218,9 @@ extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
 // ------------------------------------------------------------------------------------------------
 // attention
 // ------------------------------------------------------------------------------------------------
+#ifndef HMVIT_DENSE_TC_DEFAULT
+#define HMVIT_DENSE_TC_DEFAULT 0
+#endif
 // timing aid: 1 = only the warp + compaction pass, 2 = only the dense attention pass (on tiles left by an earlier call)
 static int g_split_phase = 0;
 extern "C" int hmvit_debug_split_phase(int phase) { g_split_phase = phase; return HMVIT_OK; }
@@ -245,14 +249,19 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
   // warp-specialised tcgen05 / TMEM kernel (attn_tc.cuh) is selected with HMVIT_ATTN_IMPL=tc and is kept
   // parity-tested (profiles/r1_attention_study.md explains what bounds it).
   static bool legacy = true;
+  static bool dense_tc = false;      // HMVIT_DENSE_IMPL=tc: second launch of the split form on tcgen05 (attn_dense_tc.cuh)
   std::call_once(once, [] {
     const char* impl = getenv("HMVIT_ATTN_IMPL");
     legacy = !(impl != nullptr && strcmp(impl, "tc") == 0);
+    const char* dimpl = getenv("HMVIT_DENSE_IMPL");
+    dense_tc = HMVIT_DENSE_TC_DEFAULT ? !(dimpl != nullptr && strcmp(dimpl, "mma") == 0) : (dimpl != nullptr && strcmp(dimpl, "tc") == 0);
     attr_err = cudaFuncSetAttribute(group_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(group_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg::SMEM_BYTES);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(dense_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dense_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseTcCfg::SMEM_BYTES);
   });
   HMVIT_CHECK_CUDA(attr_err);
   AttnParams p;
@@ -277,10 +286,14 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
     sp.vc = ws; ws += tile_bytes;
     sp.nvis = reinterpret_cast<int*>(ws); ws += (BL * G * 4 + 255) / 256 * 256;
     sp.slots = ws;
+    sp.tc_layout = dense_tc ? 1 : 0;
     dim3 grid_c(static_cast<unsigned>(G), a->B * a->L);
     if (g_split_phase != 2) warp_compact_kernel<<<grid_c, kCompactThreads, 0, static_cast<cudaStream_t>(stream)>>>(sp);
     HMVIT_CHECK_CUDA(cudaGetLastError());
-    if (g_split_phase != 1) dense_attn_kernel<<<grid, kDenseThreads, kDenseSmem, static_cast<cudaStream_t>(stream)>>>(sp);
+    if (g_split_phase != 1) {
+      if (dense_tc) dense_attn_tc_kernel<<<grid, DenseTcCfg::THREADS, DenseTcCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(sp);
+      else dense_attn_kernel<<<grid, kDenseThreads, kDenseSmem, static_cast<cudaStream_t>(stream)>>>(sp);
+    }
     HMVIT_CHECK_CUDA(cudaGetLastError());
     return HMVIT_OK;
   }
@@ -659,6 +672,10 @@ extern "C" int hmvit_debug_attn_ts(unsigned long long* host_out /* [8][8][4] */)
 }
 extern "C" int hmvit_debug_tc_ts(unsigned long long* host_out /* [8][3][64] */) {
   HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_tc_ts, sizeof(unsigned long long) * 8 * 3 * 64));
+  return HMVIT_OK;
+}
+extern "C" int hmvit_debug_dtc_ts(unsigned long long* host_out /* [8][4][32] */) {
+  HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_dtc_ts, sizeof(unsigned long long) * 8 * 4 * 32));
   return HMVIT_OK;
 }
 extern "C" int hmvit_debug_qkv_ts(unsigned long long* host_out /* [3][512] */) {

@@ -32,6 +32,8 @@ struct SplitParams {
   uint8_t* vc;                 // same for values
   int* nvis;                   // [B*L][G] visible keys of the (ego, group)
   uint8_t* slots;              // [B*L][G][L*64] group slot (0..63) of every compacted key
+  int tc_layout;               // tile image: 0 = [64 keys][256 B] XOR-swizzled (ldmatrix, dense_attn_kernel);
+                               // 1 = [2 head pairs][64 keys][128 B] UMMA SWIZZLE_128B (dense_attn_tc_kernel)
 };
 
 struct CRec { short x0, y0; uint32_t w01, w23, meta; };    // meta = source j | slot << 8
@@ -164,7 +166,8 @@ __global__ void __launch_bounds__(kCompactThreads, 4) warp_compact_kernel(const 
         vo.z = hfma2_bf16(w2, vv[q].z, vo.z); vo.w = hfma2_bf16(w2, vv[q].w, vo.w);
       }
     }
-    const size_t o = static_cast<size_t>((pos >> 6) * 2 + hg) * kBlobBytes + tile_off(pos & 63, u16);
+    const size_t o = static_cast<size_t>((pos >> 6) * 2 + hg) * kBlobBytes +
+                     (sp.tc_layout ? (u16 >> 3) * 8192 + sw128_offset(pos & 63, u16 & 7) : tile_off(pos & 63, u16));
     *reinterpret_cast<uint4*>(kdst + o) = ko;
     *reinterpret_cast<uint4*>(vdst + o) = vo;
   }

@@ -173,6 +173,10 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         uint32_t r0[32], r1[32];
         tmem_ld32(tmem_base + lane_base + Cfg::TM_ACC + buf * Cfg::BN + chh * 64, r0);
         tmem_ld32(tmem_base + lane_base + Cfg::TM_ACC + buf * Cfg::BN + chh * 64 + 32, r1);
+        // Shared-memory loads are requested one step ahead of their use (volatile asm keeps the order): under the
+        // MMA's operand traffic an LDS takes ~150 cycles, and a load-use pair per step left 8 + 3 of those
+        // exposed per chunk (ncu source view: short-scoreboard stalls on the first FADD / STG after each LDS)
+        float4 b0 = lds_f4(bb), b1 = lds_f4(bb + 4);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&acc_empty[buf]);               // accumulator columns are in registers: the MMA warp may refill the buffer
@@ -180,24 +184,41 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8) {
           const uint32_t* r = (k8 < 4) ? (r0 + k8 * 8) : (r1 + (k8 - 4) * 8);
-          const float4 b0 = *reinterpret_cast<const float4*>(bb + k8 * 8);
-          const float4 b1 = *reinterpret_cast<const float4*>(bb + k8 * 8 + 4);
+          float4 n0 = b0, n1 = b1;
+          if (k8 < 7) { n0 = lds_f4(bb + (k8 + 1) * 8); n1 = lds_f4(bb + (k8 + 1) * 8 + 4); }
           uint4 pk;
           pk.x = pack_bf16x2(__uint_as_float(r[0]) + b0.x, __uint_as_float(r[1]) + b0.y);
           pk.y = pack_bf16x2(__uint_as_float(r[2]) + b0.z, __uint_as_float(r[3]) + b0.w);
           pk.z = pack_bf16x2(__uint_as_float(r[4]) + b1.x, __uint_as_float(r[5]) + b1.y);
           pk.w = pack_bf16x2(__uint_as_float(r[6]) + b1.z, __uint_as_float(r[7]) + b1.w);
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((k8 ^ (lane & 7)) << 4)) = pk;
+          sts_u4(stg + lane * 128 + ((k8 ^ (lane & 7)) << 4), pk);
+          b0 = n0; b1 = n1;
         }
         __syncwarp();
         if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 3);
-        // coalesced stores: 4 rows x 128 B per instruction
+        // coalesced stores: 4 rows x 128 B per instruction; all eight staging reads are in flight before the first store
+        {
+          uint4 v[8];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int rr = it * 4 + (lane >> 3), u = lane & 7;
-          const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + ((u ^ (rr & 7)) << 4));
-          if (!(HMVIT_QKV_DBG & 1) || v.x == 0x12345678u)
-          if (tok0 + q4 * 32 + rr < p.N) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * kC + u * 8) = v;
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + (lane >> 3), u = lane & 7;
+            v[it] = lds_u4(stg + rr * 128 + ((u ^ (rr & 7)) << 4));
+          }
+          if (HMVIT_QKV_DBG & 1) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if (v[it].x == 0x12345678u) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(it * 4 + (lane >> 3)) * kC + (lane & 7) * 8) = v[it];
+          } else if (tok0 + Cfg::BM <= p.N) {        // whole tile inside the agent's token range (the common case)
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              *reinterpret_cast<uint4*>(obase + static_cast<size_t>(it * 4 + (lane >> 3)) * kC + (lane & 7) * 8) = v[it];
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int rr = it * 4 + (lane >> 3);
+              if (tok0 + q4 * 32 + rr < p.N) *reinterpret_cast<uint4*>(obase + static_cast<size_t>(rr) * kC + (lane & 7) * 8) = v[it];
+            }
+          }
         }
         __syncwarp();
         if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 4);
@@ -308,7 +329,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
           for (int c0 = c_lo; c0 < c_lo + CPT; c0 += 64) {
             float xv[64];
 #pragma unroll
-            for (int e = 0; e < 64; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+            for (int e = 0; e < 64; ++e) xv[e] = __ldg(src + (c0 + e) * p.N);       // row clamped to a valid token: always in bounds
 #pragma unroll
             for (int e = 0; e < 64; ++e) { const float d = xv[e] - s0; sum += d; sq += d * d; }
           }
@@ -334,7 +355,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
       for (int c0 = c_lo; c0 < c_lo + CPT; c0 += 64) {
         float xv[64];
 #pragma unroll
-        for (int e = 0; e < 64; ++e) xv[e] = (valid && !(HMVIT_QKV_DBG & 8)) ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+        for (int e = 0; e < 64; ++e) xv[e] = !(HMVIT_QKV_DBG & 8) ? __ldg(src + (c0 + e) * p.N) : 0.f;   // 32-bit offsets: 256 N < 2^31
         if constexpr (kLN) {
           if (affine) {
 #pragma unroll
@@ -343,10 +364,10 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
 #pragma unroll
             for (int e = 0; e < 64; ++e) xv[e] = fmaf(xv[e], rstd, nmr);
           }
-          if (!valid) {
+        }
+        if (!valid) {
 #pragma unroll
-            for (int e = 0; e < 64; ++e) xv[e] = 0.f;
-          }
+          for (int e = 0; e < 64; ++e) xv[e] = 0.f;
         }
         if (!waited) {
           if (pidx == 0) QKV_TS(2, ti * 4 + 1);
