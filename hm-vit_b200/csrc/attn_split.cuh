@@ -346,6 +346,8 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
     for (int hh = 0; hh < kHPW; ++hh) {
       const int hd = h0 + hh;                                   // head within the head group
       const float* bh = sBias + hd * kBiasStride + bias_q;
+      // (adding the bias after the MMAs instead of starting the accumulators from it, so that the tensor-core chain
+      //  does not wait on shared memory, was measured slower: 0.382 vs 0.368 ms)
       float sacc[8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {

@@ -147,7 +147,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         for (int c0 = 0; c0 < kC; c0 += 32) {
           float xv[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+          for (int e = 0; e < 32; ++e) xv[e] = __ldg(src + (c0 + e) * p.N);
 #pragma unroll
           for (int e = 0; e < 32; ++e) { const float d = xv[e] - s0; sum += d; sq += d * d; }
         }
@@ -165,13 +165,17 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       for (int c0 = 0; c0 < kC; c0 += 32) {
         float xv[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) xv[e] = valid ? __ldg(src + static_cast<size_t>(c0 + e) * p.N) : 0.f;
+        for (int e = 0; e < 32; ++e) xv[e] = __ldg(src + (c0 + e) * p.N);
         if constexpr (PRO == PRO_CM_LN) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const float z = (xv[e] - mean) * rstd;
-            xv[e] = valid ? (affine ? z * __ldg(gam + c0 + e) + __ldg(bet + c0 + e) : z) : 0.f;
+            xv[e] = affine ? z * __ldg(gam + c0 + e) + __ldg(bet + c0 + e) : z;
           }
+        }
+        if (!valid) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) xv[e] = 0.f;
         }
 #pragma unroll
         for (int uu = 0; uu < UPB; ++uu) {
@@ -216,11 +220,12 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
                                  (c & 1) * Cfg::BN + q * 32;
 #pragma unroll
             for (int k = 0; k < 32; k += 8) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + k)), b1 = __ldg(reinterpret_cast<const float4*>(bias + k + 4));
               uint4 pk;
-              pk.x = pack_bf16x2(__uint_as_float(r[k + 0]) + __ldg(bias + k + 0), __uint_as_float(r[k + 1]) + __ldg(bias + k + 1));
-              pk.y = pack_bf16x2(__uint_as_float(r[k + 2]) + __ldg(bias + k + 2), __uint_as_float(r[k + 3]) + __ldg(bias + k + 3));
-              pk.z = pack_bf16x2(__uint_as_float(r[k + 4]) + __ldg(bias + k + 4), __uint_as_float(r[k + 5]) + __ldg(bias + k + 5));
-              pk.w = pack_bf16x2(__uint_as_float(r[k + 6]) + __ldg(bias + k + 6), __uint_as_float(r[k + 7]) + __ldg(bias + k + 7));
+              pk.x = pack_bf16x2(__uint_as_float(r[k + 0]) + b0.x, __uint_as_float(r[k + 1]) + b0.y);
+              pk.y = pack_bf16x2(__uint_as_float(r[k + 2]) + b0.z, __uint_as_float(r[k + 3]) + b0.w);
+              pk.z = pack_bf16x2(__uint_as_float(r[k + 4]) + b1.x, __uint_as_float(r[k + 5]) + b1.y);
+              pk.w = pack_bf16x2(__uint_as_float(r[k + 6]) + b1.z, __uint_as_float(r[k + 7]) + b1.w);
               *reinterpret_cast<uint4*>(dst + k) = pk;
             }
           }
@@ -232,12 +237,18 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
             if constexpr (EPI == EPI_CM_RESID) res = p.resid_cm + static_cast<size_t>(a) * kC * p.N + static_cast<size_t>(n0) * p.N + tok;
             float rv[32];
 #pragma unroll
-            for (int k = 0; k < 32; ++k) rv[k] = (EPI == EPI_CM_RESID) ? res[static_cast<size_t>(k) * p.N] : 0.f;
+            for (int k = 0; k < 32; ++k) rv[k] = (EPI == EPI_CM_RESID) ? res[k * p.N] : 0.f;     // 32-bit offsets: 256 N < 2^31
+            float bq[32];
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + k));
+              bq[k] = b4.x; bq[k + 1] = b4.y; bq[k + 2] = b4.z; bq[k + 3] = b4.w;
+            }
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
-              float v = __uint_as_float(r[k]) + __ldg(bias + k) + rv[k];
+              float v = __uint_as_float(r[k]) + bq[k] + rv[k];
               if constexpr (EPI == EPI_CM_GELU) v = tf32_rn(gelu_erf(v));
-              dst[static_cast<size_t>(k) * p.N] = v;
+              dst[k * p.N] = v;
             }
           }
         }
@@ -262,11 +273,13 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
     }
   } else {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    // whole warp converged, one elected lane issues (operands stay in uniform registers)
+    {
       constexpr uint32_t idesc = umma_idesc(ES == 2 ? 1u : 2u, Cfg::BM, Cfg::BN);
       mbar_wait(a_full, 0);
       tc_fence_after();
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      const uint32_t tmu = __shfl_sync(0xffffffffu, tmem_base, 0);
       uint32_t it = 0;
       int ci = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
@@ -274,20 +287,23 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         const int buf = ci & 1;
         mbar_wait(&acc_empty[buf], ((ci >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * Cfg::BN;
+        const uint32_t d_tmem = tmu + buf * Cfg::BN;
         for (int kc = 0; kc < Cfg::NCHA; ++kc, ++it) {
           const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
           mbar_wait(&b_full[s], ph);
           tc_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = umma_desc_sw128(a_base + kc * Cfg::CHUNK_BYTES + ks * 32);
-            const uint64_t bd = umma_desc_sw128(b_base + s * Cfg::CHUNK_BYTES + ks * 32);
-            umma_ss<ES>(d_tmem, ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t ad = umma_desc_sw128(a_base + kc * Cfg::CHUNK_BYTES + ks * 32);
+              const uint64_t bd = umma_desc_sw128(b_base + s * Cfg::CHUNK_BYTES + ks * 32);
+              umma_ss<ES>(d_tmem, ad, bd, idesc, (kc | ks) != 0 ? 1u : 0u);
+            }
+            umma_commit(&b_empty[s]);
+            if (kc == Cfg::NCHA - 1) umma_commit(&acc_full[buf]);
           }
-          umma_commit(&b_empty[s]);
+          __syncwarp();
         }
-        umma_commit(&acc_full[buf]);
         ++ci;
       }
     }

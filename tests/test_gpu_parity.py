@@ -38,6 +38,16 @@ def test_gpu_check_single_kernel_attention(name):
     _run_with_env(name, HMVIT_ATTN_SPLIT="0")
 
 
+DENSE_TC_CHECKS = ["attention_golden", "fusion_golden", "fusion_config2_scene", "ragged_batch", "fusion_properties"]
+
+
+@pytest.mark.parametrize("name", DENSE_TC_CHECKS)
+def test_gpu_check_tcgen05_dense_attention(name):
+    """Split attention with its second launch on tcgen05 / TMEM (csrc/attn_dense_tc.cuh, HMVIT_DENSE_IMPL=tc) instead of
+    the default mma.sync dense kernel.  The switch is read once per process, hence the subprocess."""
+    _run_with_env(name, HMVIT_DENSE_IMPL="tc")
+
+
 TC_CHECKS = ["attention_golden", "fusion_golden", "fusion_config2_scene", "ragged_batch", "fusion_properties"]
 
 
