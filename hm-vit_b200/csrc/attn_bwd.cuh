@@ -19,7 +19,16 @@
 #include "attn.cuh"
 #include <mma.h>
 
+#ifndef HMVIT_BWD_DBG   // bottleneck-hunting builds only (results are wrong): 1 no shared bias-gradient atomics, 2 no global scatter
+#define HMVIT_BWD_DBG 0
+#endif
+
 namespace hmvit {
+
+// 128-bit vector reduction into global memory (sm_90+): one instruction adds four consecutive fp32 values
+HMVIT_DEVINL void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 struct AttnBwdParams {
   int B, L, H, W;
@@ -48,7 +57,7 @@ struct AttnBwdCfg {
   static constexpr int OFF_SCR = 4 * TILE_BYTES;
   static constexpr int OFF_BIAS = OFF_SCR + 8 * SCR_BYTES;        // [4][232] fp32, log2 domain
   static constexpr int OFF_BGRAD = OFF_BIAS + kHG * kBiasStride * 4;
-  static constexpr int OFF_D = OFF_BGRAD + kHG * kBiasStride * 4; // [4][64]
+  static constexpr int OFF_D = OFF_BGRAD + 8 * kBiasStride * 4;   // bias gradient: one private [232] table per warp; D: [4][64]
   static constexpr int OFF_LSE = OFF_D + kHG * kS * 4;            // [4][64]
   static constexpr int OFF_TAP = OFF_LSE + kHG * kS * 4;
   static constexpr int OFF_VIS = OFF_TAP + kMaxSrc * kS * static_cast<int>(sizeof(TapRec));
@@ -116,6 +125,7 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
       const int idx = e >> 2, h = e & 3;
       sBias[h * kBiasStride + idx] = __ldg(p.bias_table + idx * kHeads + hgc * kHG + h) * 1.4426950408889634f;
       sBgrad[h * kBiasStride + idx] = 0.f;
+      sBgrad[(h + 4) * kBiasStride + idx] = 0.f;
     }
   }
 
@@ -196,7 +206,7 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
       }
       __syncthreads();
 
-      float bsum_k = 0.f, bsum_v = 0.f;
+      float4 bsum_k4 = make_float4(0.f, 0.f, 0.f, 0.f), bsum_v4 = make_float4(0.f, 0.f, 0.f, 0.f);   // lane: 4 channels, keys = lane / 8 (mod 4)
       for (int kc = kh * 2; kc < kh * 2 + 2; ++kc) {
         // ---- S = Q_h Kg_h^T, dP = dO_h Vg_h^T for 64 queries x 16 keys ----
 #pragma unroll
@@ -219,19 +229,29 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
         }
         __syncwarp();
         // ---- probabilities and logit gradients ----
+        // The relative position bias gradient goes into a table PRIVATE to this warp with plain read-modify-writes
+        // (shared-memory float atomics cost 22 % of the kernel).  Lane mapping: lanes 0-15 take query row s, lanes
+        // 16-31 row (s + 16) ^ 1 -- two window rows further down, column parity flipped: the 32 (query, key) pairs
+        // of one step then hit 32 different table entries and conflict-free banks of the [64][16] scratch tiles.
+        float* sBgW = sBgrad + warp * kBiasStride;
 #pragma unroll 4
         for (int e = 0; e < 32; ++e) {
-          const int idx = e * 32 + lane, s = idx >> 4, kk = idx & 15, sp = kc * 16 + kk;
+          const int sA = (e >> 4) * 32 + (e & 15);
+          const int s = lane < 16 ? sA : ((sA + 16) ^ 1);
+          const int kk = lane & 15, idx = s * 16 + kk, sp = kc * 16 + kk;
           const TapRec rec = sTap[sp];
           float pr = 0.f, dsn = 0.f;
           if ((rec.w01 | rec.w23) != 0u) {
             const int rel = ((s >> 3) - (sp >> 3) + 7) * 15 + ((s & 7) - (sp & 7) + 7);
             pr = exp2f(sS[idx] + sBias[hl * kBiasStride + rel] - sLse[hl * kS + s]);
             dsn = pr * (sdP[idx] - sD[hl * kS + s]);
-            atomicAdd(&sBgrad[hl * kBiasStride + rel], dsn);
+#if !(HMVIT_BWD_DBG & 1)
+            sBgW[rel] += dsn;
+#endif
           }
           sPb[idx] = __float2bfloat16(pr);
           sdSb[idx] = __float2bfloat16(dsn * 0.69314718055994530942f);
+          __syncwarp();                                          // the next step may touch the same table entry from another lane
         }
         __syncwarp();
         // ---- dQ_h += dS Kg_h ----
@@ -273,29 +293,51 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
           }
         }
         __syncwarp();
-        // ---- bilinear scatter of the 16 keys of this chunk (lane == channel of the head) ----
+        // ---- bilinear scatter of the 16 keys of this chunk: 8 lanes x 4 channels per key, four keys per pass,
+        //      128-bit vector reductions (red.global.add.v4.f32): a quarter of the atomic instructions of a
+        //      lane-per-channel scatter, which bound this kernel (1.7 G scalar atomics per launch at config 2) ----
         {
-          float* dkp = p.dk + (static_cast<size_t>(te) * R + static_cast<size_t>(b * p.L + j) * N) * kC + ch;
-          float* dvp = p.dv + (static_cast<size_t>(te) * R + static_cast<size_t>(b * p.L + j) * N) * kC + ch;
-          for (int kk = 0; kk < 16; ++kk) {
+          const int cg = lane & 7, kg = lane >> 3;
+          const size_t rbase = (static_cast<size_t>(te) * R + static_cast<size_t>(b * p.L + j) * N) * kC + hgc * 128 + hl * 32 + cg * 4;
+          float* dkp = p.dk + rbase;
+          float* dvp = p.dv + rbase;
+#pragma unroll
+          for (int k4 = 0; k4 < 16; k4 += 4) {
+            const int kk = k4 + kg;
             const TapRec rec = sTap[kc * 16 + kk];
             if ((rec.w01 | rec.w23) == 0u) continue;
-            const float gk = sS[kk * 32 + lane], gv = sdP[kk * 32 + lane];
-            bsum_k += gk; bsum_v += gv;
+            const float4 gk = *reinterpret_cast<const float4*>(sS + kk * 32 + cg * 4);
+            const float4 gv = *reinterpret_cast<const float4*>(sdP + kk * 32 + cg * 4);
+            bsum_k4.x += gk.x; bsum_k4.y += gk.y; bsum_k4.z += gk.z; bsum_k4.w += gk.w;
+            bsum_v4.x += gv.x; bsum_v4.y += gv.y; bsum_v4.z += gv.z; bsum_v4.w += gv.w;
             const float wq[4] = {bf16_lo(rec.w01), bf16_hi(rec.w01), bf16_lo(rec.w23), bf16_hi(rec.w23)};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (wq[q] == 0.f) continue;
               const size_t off = static_cast<size_t>((rec.y0 + (q >> 1)) * p.W + rec.x0 + (q & 1)) * kC;
-              atomicAdd(dkp + off, wq[q] * gk);
-              atomicAdd(dvp + off, wq[q] * gv);
+#if !(HMVIT_BWD_DBG & 2)
+              red_add_v4(dkp + off, wq[q] * gk.x, wq[q] * gk.y, wq[q] * gk.z, wq[q] * gk.w);
+              red_add_v4(dvp + off, wq[q] * gv.x, wq[q] * gv.y, wq[q] * gv.z, wq[q] * gv.w);
+#endif
             }
           }
         }
         __syncwarp();                                            // scratch is rewritten by the next chunk
       }
-      atomicAdd(p.dbk + (te * 2 + tj) * kC + ch, bsum_k);
-      atomicAdd(p.dbv + (te * 2 + tj) * kC + ch, bsum_v);
+      {
+        // folded-bias gradients: sum the four key sub-groups (lanes l, l ^ 8, l ^ 16, l ^ 24 hold the same 4 channels)
+        float* bk = &bsum_k4.x; float* bv = &bsum_v4.x;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          bk[e] += __shfl_xor_sync(0xffffffffu, bk[e], 8);  bk[e] += __shfl_xor_sync(0xffffffffu, bk[e], 16);
+          bv[e] += __shfl_xor_sync(0xffffffffu, bv[e], 8);  bv[e] += __shfl_xor_sync(0xffffffffu, bv[e], 16);
+        }
+        if (lane < 8) {
+          const int ch4 = hgc * 128 + hl * 32 + lane * 4;
+          red_add_v4(p.dbk + (te * 2 + tj) * kC + ch4, bsum_k4.x, bsum_k4.y, bsum_k4.z, bsum_k4.w);
+          red_add_v4(p.dbv + (te * 2 + tj) * kC + ch4, bsum_v4.x, bsum_v4.y, bsum_v4.z, bsum_v4.w);
+        }
+      }
       __syncthreads();                                           // sK / sV are rewritten for the next source
     }
   }
@@ -307,15 +349,17 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) wmma::store_matrix_sync(sS + (mt * 16) * 32 + nt * 16, dq[mt][nt], 32, wmma::mem_row_major);
   __syncwarp();
-  for (int s = 0; s < kS; ++s) {
+  for (int s4 = 0; s4 < kS; s4 += 4) {
+    const int s = s4 + (lane >> 3), cg = lane & 7;
     int r, c; group_token(p.kind, gy, gx, s, p.H, p.W, r, c);
-    atomicAdd(p.dq + (static_cast<size_t>(a) * N + r * p.W + c) * kC + ch, sS[s * 32 + lane]);
+    const float4 g = *reinterpret_cast<const float4*>(sS + s * 32 + cg * 4);
+    red_add_v4(p.dq + (static_cast<size_t>(a) * N + r * p.W + c) * kC + hgc * 128 + hl * 32 + cg * 4, g.x, g.y, g.z, g.w);
   }
   // ---- relative position bias gradient ----
   __syncthreads();
   for (int e = threadIdx.x; e < 225 * kHG; e += Cfg::THREADS) {
     const int idx = e >> 2, h = e & 3;
-    const float g = sBgrad[h * kBiasStride + idx];
+    const float g = sBgrad[h * kBiasStride + idx] + sBgrad[(h + 4) * kBiasStride + idx];   // the two key-half warps of head h
     if (g != 0.f) atomicAdd(p.dbias_table + idx * kHeads + hgc * kHG + h, g);
   }
 }
