@@ -15,7 +15,7 @@ GEMM_LN_LIN_CM, GEMM_LIN_CM, GEMM_LIN_ROWS, GEMM_ROWS_LIN_CM = range(7, 11)
 EXPORTS = (
     "hmvit_abi_version", "hmvit_last_error", "hmvit_rowgemm", "hmvit_group_attn", "hmvit_warp_bilinear",
     "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
-    "hmvit_debug_probe", "hmvit_out_ffn_chain",
+    "hmvit_debug_probe", "hmvit_out_ffn_chain", "hmvit_ffn_head",
     "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
     "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes",
 )
@@ -35,6 +35,12 @@ class ChainArgs(C.Structure):
                 ("wa", C.c_void_p * 2), ("ba", C.c_void_p), ("ln_gamma", C.c_void_p), ("ln_beta", C.c_void_p),
                 ("ln_eps", C.c_float), ("w1", C.c_void_p * 2), ("b1", C.c_void_p), ("w2", C.c_void_p * 2), ("b2", C.c_void_p),
                 ("stats_out", C.c_void_p)]
+
+
+class HeadArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("N", C.c_int32), ("mode", C.c_void_p), ("record_len", C.c_void_p),
+                ("x", C.c_void_p), ("w1", C.c_void_p * 2), ("b1", C.c_void_p), ("w2", C.c_void_p * 2), ("b2", C.c_void_p),
+                ("out", C.c_void_p)]
 
 
 class AttnArgs(C.Structure):
@@ -101,6 +107,8 @@ def load():
     lib.hmvit_rowgemm.restype = C.c_int
     lib.hmvit_out_ffn_chain.argtypes = [C.POINTER(ChainArgs), C.c_void_p]
     lib.hmvit_out_ffn_chain.restype = C.c_int
+    lib.hmvit_ffn_head.argtypes = [C.POINTER(HeadArgs), C.c_void_p]
+    lib.hmvit_ffn_head.restype = C.c_int
     lib.hmvit_group_attn.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     lib.hmvit_group_attn.restype = C.c_int
     lib.hmvit_group_attn_workspace_bytes.argtypes = [C.c_int32] * 4

@@ -200,17 +200,50 @@ extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
   ChainParams p;
   p.B = a->B; p.L = a->L; p.N = a->N; p.mode = a->mode; p.record_len = a->record_len; p.tile_ego_only = a->ego_only ? 1 : 0;
   p.resid_cm = a->resid; p.out_cm = a->out; p.ba = a->ba; p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_eps = a->ln_eps;
-  p.b1 = a->b1; p.b2 = a->b2; p.stats_out = reinterpret_cast<float2*>(a->stats_out);
+  p.b1 = a->b1; p.b2 = a->b2; p.stats_out = reinterpret_cast<float2*>(a->stats_out); p.out_L = a->L;
   HMVIT_CHECK_ARG((a->ln_gamma == nullptr) == (a->ln_beta == nullptr), "chain: ln_gamma and ln_beta must both be set or both be null");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES);
   });
   HMVIT_CHECK_CUDA(attr_err);
   const long long tiles = static_cast<long long>(a->B) * a->L * ((a->N + ChainCfg::BM - 1) / ChainCfg::BM);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  chain_kernel<<<grid, ChainCfg::THREADS, ChainCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(maps, p);
+  chain_kernel<false><<<grid, ChainCfg::THREADS, ChainCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(maps, p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// typed feed-forward head on the ego rows (the chain kernel without projection, LayerNorm and residual)
+// ------------------------------------------------------------------------------------------------
+extern "C" int hmvit_ffn_head(const HmvitHeadArgs* a, void* stream) {
+  HMVIT_CHECK_ARG(a != nullptr, "ffn_head: null args");
+  HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->N > 0, "ffn_head: B, L, N must be positive");
+  HMVIT_CHECK_ARG(a->mode && a->record_len && a->x && a->out && a->w1[0] && a->w1[1] && a->b1 && a->w2[0] && a->w2[1] && a->b2,
+                  "ffn_head: null pointer");
+  ChainMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int t = 0; t < 2; ++t) {
+    int rc = make_weight_tmap(&maps.w1[t], a->w1[t], 256, 4, 256); if (rc) return rc;
+    rc = make_weight_tmap(&maps.w2[t], a->w2[t], 256, 4, 256); if (rc) return rc;
+  }
+  ChainParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = a->B; p.L = a->L; p.N = a->N; p.mode = a->mode; p.record_len = a->record_len; p.tile_ego_only = 1;
+  p.resid_cm = a->x; p.out_cm = a->out; p.out_L = 1;
+  p.ba = a->b1;                                  // unused by the head instance (staged with the other biases)
+  p.b1 = a->b1; p.b2 = a->b2; p.ln_eps = 1e-5f;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  const long long tiles = static_cast<long long>(a->B) * a->L * ((a->N + ChainCfg::BM - 1) / ChainCfg::BM);
+  const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
+  chain_kernel<true><<<grid, ChainCfg::THREADS, ChainCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(maps, p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }
@@ -393,7 +426,7 @@ static bool split_attention() {
 }
 
 extern "C" int hmvit_fusion_launch_count(int32_t num_iters, int32_t head) {
-  return num_iters * 2 * (split_attention() ? 4 : 3) + (head ? 2 : 0);
+  return num_iters * 2 * (split_attention() ? 4 : 3) + (head ? 1 : 0);
 }
 
 static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream);
@@ -504,13 +537,22 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
   if (a->head) {
     HMVIT_CHECK_ARG(a->head_w1[0] && a->head_w1[1] && a->head_w2[0] && a->head_w2[1] && a->head_b1 && a->head_b2,
                     "fusion_forward: head weights missing");
-    HmvitRowGemmArgs g;
-    memset(&g, 0, sizeof(g));
-    g.B = a->B; g.L = a->L; g.N = N; g.mode = a->mode; g.record_len = a->record_len; g.ego_only = 1; g.ln_eps = a->ln_eps;
-    g.n_out = 256; g.a = a->xres; g.w[0] = a->head_w1[0]; g.w[1] = a->head_w1[1]; g.bias = a->head_b1; g.out = hid;
-    int rc = hmvit_rowgemm(HMVIT_GEMM_HEAD1, &g, stream); if (rc) return rc;
-    g.a = hid; g.w[0] = a->head_w2[0]; g.w[1] = a->head_w2[1]; g.bias = a->head_b2; g.out = a->out;
-    rc = hmvit_rowgemm(HMVIT_GEMM_HEAD2, &g, stream); if (rc) return rc;
+    if (a->unfused) {
+      HmvitRowGemmArgs g;
+      memset(&g, 0, sizeof(g));
+      g.B = a->B; g.L = a->L; g.N = N; g.mode = a->mode; g.record_len = a->record_len; g.ego_only = 1; g.ln_eps = a->ln_eps;
+      g.n_out = 256; g.a = a->xres; g.w[0] = a->head_w1[0]; g.w[1] = a->head_w1[1]; g.bias = a->head_b1; g.out = hid;
+      int rc = hmvit_rowgemm(HMVIT_GEMM_HEAD1, &g, stream); if (rc) return rc;
+      g.a = hid; g.w[0] = a->head_w2[0]; g.w[1] = a->head_w2[1]; g.bias = a->head_b2; g.out = a->out;
+      rc = hmvit_rowgemm(HMVIT_GEMM_HEAD2, &g, stream); if (rc) return rc;
+    } else {
+      HmvitHeadArgs h;
+      memset(&h, 0, sizeof(h));
+      h.B = a->B; h.L = a->L; h.N = N; h.mode = a->mode; h.record_len = a->record_len; h.x = a->xres;
+      h.w1[0] = a->head_w1[0]; h.w1[1] = a->head_w1[1]; h.b1 = a->head_b1;
+      h.w2[0] = a->head_w2[0]; h.w2[1] = a->head_w2[1]; h.b2 = a->head_b2; h.out = a->out;
+      int rc = hmvit_ffn_head(&h, stream); if (rc) return rc;
+    }
   }
   return HMVIT_OK;
 }

@@ -49,6 +49,7 @@ struct ChainParams {
   const float* b1;             // [2][256]
   const float* b2;             // [2][256]
   float2* stats_out;           // optional [B*L][N] (mean, rstd) of every x'' row: LayerNorm statistics for the next stage
+  int out_L;                   // agent slots per scene in out_cm (L; 1 for the head, whose output is [B][256][N])
 };
 
 struct ChainMaps {             // TMA tensor maps
@@ -83,6 +84,10 @@ HMVIT_DEVINL float2 ln_combine(const float2* part, int row, float eps) {
   return make_float2(mean, rsqrtf(fmaxf(m2 * (1.0f / kC), 0.f) + eps));
 }
 
+// kHead: the typed feed-forward HEAD of the fusion module (HeteroFusion.mlp_head, bevformer_point_pillar_hetero.py:36,
+// 47-48): y = W_2 gelu(W_1 x + b_1) + b_2 on the ego rows -- the same pipeline without the output projection (P1),
+// without LayerNorm and without the residual (P3 overwrites D1 instead of accumulating onto x').
+template <bool kHead>
 __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   using Cfg = ChainCfg;
   extern __shared__ uint8_t smem_raw[];
@@ -163,46 +168,50 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
       const bool valid = tok < p.N;
       const size_t cm_off = static_cast<size_t>(a) * kC * p.N + (valid ? tok : 0);
       const float* res = p.resid_cm + cm_off + static_cast<size_t>(c0) * p.N;
-      float* dst = p.out_cm + cm_off + static_cast<size_t>(c0) * p.N;
+      const int a_out = kHead ? (a / p.L) * p.out_L : a;        // head: slot 0 of scene b -> row b of the [B][256][N] output
+      float* dst = p.out_cm + static_cast<size_t>(a_out) * kC * p.N + (valid ? tok : 0) + static_cast<size_t>(c0) * p.N;
       // ---- E1: x' = D1 + b_a + x on this group's 64 columns; the residual loads are issued before the
       //      projection MMAs have finished (and were L2-prefetched during the previous tile) ----
       float rv[64];
 #pragma unroll
       for (int k = 0; k < 64; ++k) rv[k] = (valid && !(HMVIT_CHAIN_DBG & 8)) ? res[static_cast<size_t>(k) * p.N] : 0.f;
-      if (threadIdx.x == 0) CHAIN_TS(0, ti, 0);
-      mbar_wait(d1_full, ti & 1);
-      tc_fence_after();
-      if (threadIdx.x == 0) CHAIN_TS(0, ti, 1);
-      float s0 = 0.f, sum = 0.f, sq = 0.f;
-      {
-        const float* bias = sBias + type * kC + c0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t r[16];
-          tmem_ld16(D1 + lane_base + c0 + q * 16, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const float v = __uint_as_float(r[k]) + bias[q * 16 + k] + rv[q * 16 + k];
-            if (q == 0 && k == 0) s0 = v;
-            const float d = v - s0;
-            sum += d; sq += d * d;
-            r[k] = __float_as_uint(v);
-            rv[q * 16 + k] = v;                    // x' stays in registers for the LayerNorm feed below
+      float rstd = 1.f, nmr = 0.f;
+      if constexpr (!kHead) {
+        if (threadIdx.x == 0) CHAIN_TS(0, ti, 0);
+        mbar_wait(d1_full, ti & 1);
+        tc_fence_after();
+        if (threadIdx.x == 0) CHAIN_TS(0, ti, 1);
+        float s0 = 0.f, sum = 0.f, sq = 0.f;
+        {
+          const float* bias = sBias + type * kC + c0;
+  #pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t r[16];
+            tmem_ld16(D1 + lane_base + c0 + q * 16, r);
+            tmem_ld_wait();
+  #pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float v = __uint_as_float(r[k]) + bias[q * 16 + k] + rv[q * 16 + k];
+              if (q == 0 && k == 0) s0 = v;
+              const float d = v - s0;
+              sum += d; sq += d * d;
+              r[k] = __float_as_uint(v);
+              rv[q * 16 + k] = v;                    // x' stays in registers for the LayerNorm feed below
+            }
+            tmem_st16(D1 + lane_base + c0 + q * 16, r);
           }
-          tmem_st16(D1 + lane_base + c0 + q * 16, r);
         }
+        tmem_st_wait();
+        {
+          const float md = sum * (1.0f / 64.0f);
+          sPart[gq * 128 + row] = make_float2(s0 + md, fmaxf(sq - sum * md, 0.f));     // (mean_g, M2_g)
+        }
+        tc_fence_before();
+        named_bar_sync(1, Cfg::NT);
+        tc_fence_after();
+        const float2 st = ln_combine(sPart, row, p.ln_eps);
+        rstd = st.y; nmr = -st.x * st.y;
       }
-      tmem_st_wait();
-      {
-        const float md = sum * (1.0f / 64.0f);
-        sPart[gq * 128 + row] = make_float2(s0 + md, fmaxf(sq - sum * md, 0.f));     // (mean_g, M2_g)
-      }
-      tc_fence_before();
-      named_bar_sync(1, Cfg::NT);
-      tc_fence_after();
-      const float2 st = ln_combine(sPart, row, p.ln_eps);
-      const float rstd = st.y, nmr = -st.x * st.y;
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 2);
       // ---- P2 feed: LN'(x') -> tf32 K-chunks kc = 2gq, 2gq + 1 (this group's own columns, from registers) ----
       const bool affine = p.ln_gamma != nullptr;
@@ -294,16 +303,18 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
   } else if (warp == 16) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      tma_prefetch_desc(&maps.o);
+      if constexpr (!kHead) tma_prefetch_desc(&maps.o);
       uint32_t ti = 0, itw = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int a, tok0;
         if (!tile_agent(t, a, tok0)) continue;
         const int type = p.mode[a] != 0 ? 1 : 0;
-        mbar_wait(o_empty, (ti & 1) ^ 1u);
-        mbar_arrive_expect_tx(o_full, Cfg::AO_BYTES);
-        const int row0 = a * p.N + tok0;
-        for (int kc = 0; kc < 4; ++kc) tma_load_2d(sO + kc * Cfg::CHUNK, &maps.o, o_full, kc * 64, row0);
+        if constexpr (!kHead) {
+          mbar_wait(o_empty, (ti & 1) ^ 1u);
+          mbar_arrive_expect_tx(o_full, Cfg::AO_BYTES);
+          const int row0 = a * p.N + tok0;
+          for (int kc = 0; kc < 4; ++kc) tma_load_2d(sO + kc * Cfg::CHUNK, &maps.o, o_full, kc * 64, row0);
+        }
         auto wstage = [&](const CUtensorMap* m, int c0) {
           const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
           mbar_wait(&w_empty[s], ph ^ 1u);
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
           tma_load_2d(sW + s * Cfg::WSTAGE, m, &w_full[s], c0, 0);
           ++itw;
         };
-        for (int kc = 0; kc < 4; ++kc) wstage(&maps.wa[type], kc * 64);
+        if constexpr (!kHead) for (int kc = 0; kc < 4; ++kc) wstage(&maps.wa[type], kc * 64);
         for (int j = 0; j < 8; ++j) wstage(&maps.w1[type], (2 * (j & 3) + (j >> 2)) * 32);   // same order as the MMA issuer
         for (int j = 0; j < 8; ++j) wstage(&maps.w2[type], (2 * (j & 3) + (j >> 2)) * 32);
         ++ti;
@@ -331,23 +342,25 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         CHAIN_TS(1, ti, 0);
         mbar_wait(d1_free, (ti & 1) ^ 1u);
         CHAIN_TS(1, ti, 1);
-        mbar_wait(o_full, ti & 1);
-        tc_fence_after();
-        CHAIN_TS(1, ti, 2);
-        // P1: D1 = O W_a^T   (4 weight stages of 64 K-columns, one M128 N256 K16 MMA per k-step)
-        for (int kc = 0; kc < 4; ++kc, ++itw) {
-          const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
-          mbar_wait(&w_full[s], ph);
+        if constexpr (!kHead) {
+          mbar_wait(o_full, ti & 1);
           tc_fence_after();
-          if (!(HMVIT_CHAIN_DBG & 4))
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss<2>(D1, umma_desc_sw128(o_base + kc * Cfg::CHUNK + ks * 32),
-                       umma_desc_sw128(w_base + s * Cfg::WSTAGE + ks * 32), idesc_bf16, (kc | ks) != 0 ? 1u : 0u);
-          umma_commit(&w_empty[s]);
+          CHAIN_TS(1, ti, 2);
+          // P1: D1 = O W_a^T   (4 weight stages of 64 K-columns, one M128 N256 K16 MMA per k-step)
+          for (int kc = 0; kc < 4; ++kc, ++itw) {
+            const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
+            mbar_wait(&w_full[s], ph);
+            tc_fence_after();
+            if (!(HMVIT_CHAIN_DBG & 4))
+  #pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss<2>(D1, umma_desc_sw128(o_base + kc * Cfg::CHUNK + ks * 32),
+                         umma_desc_sw128(w_base + s * Cfg::WSTAGE + ks * 32), idesc_bf16, (kc | ks) != 0 ? 1u : 0u);
+            umma_commit(&w_empty[s]);
+          }
+          umma_commit(o_empty);
+          umma_commit(d1_full);
         }
-        umma_commit(o_empty);
-        umma_commit(d1_full);
         CHAIN_TS(1, ti, 3);
         // P2: D2 = LN'(x') W_1^T      P3: D1 += gelu(.) W_2^T     (8 stages of 32 K-columns each)
         for (int phase = 0; phase < 2; ++phase) {
@@ -365,7 +378,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
             for (int ks = 0; ks < 4; ++ks)
               umma_ss<4>(dacc, umma_desc_sw128(f_base + fs * Cfg::CHUNK + ks * 32),
                          umma_desc_sw128(w_base + s * Cfg::WSTAGE + ks * 32), idesc_tf32,
-                         (phase == 1 || (j | ks) != 0) ? 1u : 0u);
+                         ((phase == 1 && !kHead) || (j | ks) != 0) ? 1u : 0u);
             umma_commit(&w_empty[s]);
             umma_commit(&f_empty[fs]);
           }

@@ -69,6 +69,19 @@ def out_ffn_chain(*, B, L, N, mode, record_len, o, resid, out, wa0, wa1, ba, w1_
     return out
 
 
+def ffn_head(*, B, L, N, mode, record_len, x, w1_0, w1_1, b1, w2_0, w2_1, b2, out):
+    """Typed feed-forward head on slot 0 of every scene (HeteroFusion.mlp_head,
+    bevformer_point_pillar_hetero.py:46-48): out[B,256,N] = W2 gelu(W1 x + b1) + b2."""
+    args = _lib.HeadArgs()
+    args.B, args.L, args.N = B, L, N
+    args.mode, args.record_len = mode.data_ptr(), record_len.data_ptr()
+    args.x, args.out = x.data_ptr(), out.data_ptr()
+    args.w1[0], args.w1[1], args.b1 = w1_0.data_ptr(), w1_1.data_ptr(), b1.data_ptr()
+    args.w2[0], args.w2[1], args.b2 = w2_0.data_ptr(), w2_1.data_ptr(), b2.data_ptr()
+    _lib.check(_lib.load().hmvit_ffn_head(C.byref(args), _stream()))
+    return out
+
+
 _ATTN_WS = {}
 
 

@@ -111,6 +111,26 @@ typedef struct {
 
 int hmvit_out_ffn_chain(const HmvitChainArgs* args, void* stream);
 
+/* ---- typed feed-forward head on the ego rows ------------------------------------------------------
+ * Replaces HeteroFusion.mlp_head applied to the ego slice
+ *   opencood/models/bevformer_point_pillar_hetero.py:36, 46-48
+ *   (HeteroFeedForward, opencood/models/base_transformer.py:180-192: Linear - GELU(erf) - Linear per agent type,
+ *    no LayerNorm, no residual).
+ * out[b] = W_2 gelu(W_1 x[b, slot 0] + b_1) + b_2, one launch of the chain kernel's head instance (tf32 operands). */
+typedef struct {
+  int32_t B, L, N;
+  const int32_t* mode;
+  const int32_t* record_len;
+  const float* x;             /* fp32 cm [B*L][256][N]; only slot 0 of every scene is read */
+  const void* w1[2];          /* fp32 (tf32) [256][256] per type */
+  const float* b1;            /* [2][256] */
+  const void* w2[2];          /* fp32 (tf32) [256][256] per type */
+  const float* b2;            /* [2][256] */
+  float* out;                 /* fp32 cm [B][256][N] */
+} HmvitHeadArgs;
+
+int hmvit_ffn_head(const HmvitHeadArgs* args, void* stream);
+
 /* ---- fused warp + mask + multi-agent window / grid attention ---------------------------------------
  * Replaces HeteroFusionBlock.warp_features + the ego loop around HeteroAttention.forward
  *   opencood/models/sub_modules/hetero_fusion.py:338-361, 373-397 (window) / 412-440 (grid), 187-277
