@@ -22,6 +22,12 @@
 #include "common.cuh"
 #include <cuda.h>
 
+#ifndef HMVIT_CHAIN_INC     // registers per thread of the transform warpgroups / of the TMA + MMA warpgroup after rebalancing
+#define HMVIT_CHAIN_INC 104
+#endif
+#ifndef HMVIT_CHAIN_DEC
+#define HMVIT_CHAIN_DEC 40
+#endif
 #ifndef HMVIT_CHAIN_DBG    // bottleneck-hunting builds only (results are wrong): 1 no stores, 2 no weight TMA, 4 no MMA, 8 no residual loads
 #define HMVIT_CHAIN_DBG 0
 #endif
@@ -72,7 +78,7 @@ struct ChainCfg {
   static constexpr int BIAS_BYTES = 3 * 2 * 256 * 4;   // ba | b1 | b2, both types: read by every transform thread
   static constexpr int SMEM_BYTES = AO_BYTES + NF * CHUNK + NS * WSTAGE + PART_BYTES + BIAS_BYTES + 256 + 1024;
   static constexpr int NT = 512;                      // transform threads
-  static constexpr int THREADS = NT + 64;
+  static constexpr int THREADS = NT + 128;            // 16 transform warps + one warpgroup holding the TMA and MMA warps (2 idle)
 };
 
 // combine four (mean, M2) partials over 64 values each -> (mean, rstd) over 256
@@ -141,6 +147,9 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
 
   if (warp < 16) {
     // ============================ transform / epilogue warps ============================
+    // register rebalancing between warpgroups: the four transform warpgroups take 104 registers per thread,
+    // the warpgroup of the TMA / MMA warps gives its share back (640 x 96 at launch : the pool is per CTA, 128 x 56 released >= 512 x 8 requested)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HMVIT_CHAIN_INC));
     const int gq = warp >> 2;                          // column / chunk group
     const int row = (warp & 3) * 32 + lane;            // token row == TMEM lane
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -300,7 +309,9 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
       ++ti;
       t = t_next;
     }
-  } else if (warp == 16) {
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HMVIT_CHAIN_DEC));     // one instruction for the whole warpgroup (warps 16-19)
+  if (warp == 16) {
     // ============================ TMA producer ============================
     if (lane == 0) {
       if constexpr (!kHead) tma_prefetch_desc(&maps.o);
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         ++ti;
       }
     }
-  } else {
+  } else if (warp == 17) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       constexpr uint32_t idesc_bf16 = umma_idesc(1u, 128, 256);
@@ -388,6 +399,8 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         ++ti;
       }
     }
+  }
+
   }
 
   tc_fence_before();
