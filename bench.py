@@ -191,11 +191,11 @@ def kernel_breakdown(pkg, net, inp, iters=3):
                     split_phase(2); timed("group_attn/dense_attn", attn)
                     split_phase(0)
                 timed("out_ffn_chain", lambda: ops.out_ffn_chain(o=att, resid=xsrc, out=xres, wa0=w["wa0"], wa1=w["wa1"], ba=w["ba"],
-                                                                 w1_0=w["w1_0"], w1_1=w["w1_1"], b1=w["b1"], w2_0=w["w2_0"],
-                                                                 w2_1=w["w2_1"], b2=w["b2"], ego_only=dead, stats_out=stats,
+                                                                 w1_0=w["w1h_0"], w1_1=w["w1h_1"], b1=w["b1"], w2_0=w["w2h_0"],
+                                                                 w2_1=w["w2h_1"], b2=w["b2"], ego_only=dead, stats_out=stats,
                                                                  **common))
-        timed("head_gemm", lambda: ops.ffn_head(x=xres, w1_0=hp["w1_0"], w1_1=hp["w1_1"], b1=hp["b1"], w2_0=hp["w2_0"],
-                                                w2_1=hp["w2_1"], b2=hp["b2"], out=out, **common))
+        timed("head_gemm", lambda: ops.ffn_head(x=xres, w1_0=hp["w1h_0"], w1_1=hp["w1h_1"], b1=hp["b1"], w2_0=hp["w2h_0"],
+                                                w2_1=hp["w2h_1"], b2=hp["b2"], out=out, **common))
     torch.cuda.synchronize()
     res = {}
     for name, evs in acc.items():

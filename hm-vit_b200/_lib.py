@@ -75,7 +75,7 @@ class StageWeights(C.Structure):
                 ("wa", C.c_void_p * 2), ("ba", C.c_void_p),
                 ("ln1_g", C.c_void_p), ("ln1_b", C.c_void_p), ("ln2_g", C.c_void_p), ("ln2_b", C.c_void_p),
                 ("w1", C.c_void_p * 2), ("b1", C.c_void_p), ("w2", C.c_void_p * 2), ("b2", C.c_void_p),
-                ("bias_table", C.c_void_p)]
+                ("bias_table", C.c_void_p), ("w1h", C.c_void_p * 2), ("w2h", C.c_void_p * 2)]
 
 
 class FusionArgs(C.Structure):
@@ -85,7 +85,8 @@ class FusionArgs(C.Structure):
                 ("cav_mask", C.c_void_p), ("cell", C.c_double), ("ln_eps", C.c_float),
                 ("stage", StageWeights * 2),
                 ("head_w1", C.c_void_p * 2), ("head_b1", C.c_void_p), ("head_w2", C.c_void_p * 2), ("head_b2", C.c_void_p),
-                ("xres", C.c_void_p), ("workspace", C.c_void_p), ("out", C.c_void_p)]
+                ("xres", C.c_void_p), ("workspace", C.c_void_p), ("out", C.c_void_p),
+                ("head_w1h", C.c_void_p * 2), ("head_w2h", C.c_void_p * 2)]
 
 
 _lib = None
@@ -138,7 +139,7 @@ def load():
     for fn in ("hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
                "hmvit_bwd_wgrad", "hmvit_group_attn_bwd"):
         getattr(lib, fn).restype = C.c_int
-    if lib.hmvit_abi_version() != 3:
+    if lib.hmvit_abi_version() != 4:
         raise ImportError("libhmvit_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

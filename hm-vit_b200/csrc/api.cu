@@ -47,14 +47,14 @@ static void load_encode() {
       qres == cudaDriverEntryPointSuccess)
     g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
 }
-static int make_weight_tmap(CUtensorMap* map, const void* w, long long n_out, int es, int box_rows = 128) {
+static int make_weight_tmap(CUtensorMap* map, const void* w, long long n_out, int es, int box_rows = 128, bool f16 = false) {
   std::call_once(g_encode_once, load_encode);
   if (!g_encode) return fail(HMVIT_ERR_CUDA, "hmvit: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {256, static_cast<cuuint64_t>(n_out)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(256) * es};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+  CUresult r = g_encode(map, es == 2 ? (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                         const_cast<void*>(w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(HMVIT_ERR_CUDA, "hmvit: cuTensorMapEncodeTiled failed (" + std::to_string(int(r)) + ")");
@@ -194,8 +194,8 @@ extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
   int rc = make_weight_tmap(&maps.o, a->o, static_cast<long long>(a->B) * a->L * a->N, 2); if (rc) return rc;
   for (int t = 0; t < 2; ++t) {
     rc = make_weight_tmap(&maps.wa[t], a->wa[t], 256, 2, 256); if (rc) return rc;
-    rc = make_weight_tmap(&maps.w1[t], a->w1[t], 256, 4, 256); if (rc) return rc;
-    rc = make_weight_tmap(&maps.w2[t], a->w2[t], 256, 4, 256); if (rc) return rc;
+    rc = make_weight_tmap(&maps.w1[t], a->w1[t], 256, 2, 256, true); if (rc) return rc;
+    rc = make_weight_tmap(&maps.w2[t], a->w2[t], 256, 2, 256, true); if (rc) return rc;
   }
   ChainParams p;
   p.B = a->B; p.L = a->L; p.N = a->N; p.mode = a->mode; p.record_len = a->record_len; p.tile_ego_only = a->ego_only ? 1 : 0;
@@ -226,8 +226,8 @@ extern "C" int hmvit_ffn_head(const HmvitHeadArgs* a, void* stream) {
   ChainMaps maps;
   memset(&maps, 0, sizeof(maps));
   for (int t = 0; t < 2; ++t) {
-    int rc = make_weight_tmap(&maps.w1[t], a->w1[t], 256, 4, 256); if (rc) return rc;
-    rc = make_weight_tmap(&maps.w2[t], a->w2[t], 256, 4, 256); if (rc) return rc;
+    int rc = make_weight_tmap(&maps.w1[t], a->w1[t], 256, 2, 256, true); if (rc) return rc;
+    rc = make_weight_tmap(&maps.w2[t], a->w2[t], 256, 2, 256, true); if (rc) return rc;
   }
   ChainParams p;
   memset(&p, 0, sizeof(p));
@@ -527,7 +527,8 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
         c.B = a->B; c.L = a->L; c.N = N; c.mode = a->mode; c.record_len = a->record_len; c.ego_only = dead;
         c.o = att; c.resid = xsrc; c.out = a->xres;
         c.wa[0] = w.wa[0]; c.wa[1] = w.wa[1]; c.ba = w.ba; c.ln_gamma = w.ln2_g; c.ln_beta = w.ln2_b; c.ln_eps = a->ln_eps;
-        c.w1[0] = w.w1[0]; c.w1[1] = w.w1[1]; c.b1 = w.b1; c.w2[0] = w.w2[0]; c.w2[1] = w.w2[1]; c.b2 = w.b2;
+        HMVIT_CHECK_ARG(w.w1h[0] && w.w1h[1] && w.w2h[0] && w.w2h[1], "fusion_forward: fp16 feed-forward weights (w1h / w2h) missing");
+        c.w1[0] = w.w1h[0]; c.w1[1] = w.w1h[1]; c.b1 = w.b1; c.w2[0] = w.w2h[0]; c.w2[1] = w.w2h[1]; c.b2 = w.b2;
         c.stats_out = stats;
         rc = hmvit_out_ffn_chain(&c, stream); if (rc) return rc;
         have_stats = true;
@@ -549,8 +550,9 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
       HmvitHeadArgs h;
       memset(&h, 0, sizeof(h));
       h.B = a->B; h.L = a->L; h.N = N; h.mode = a->mode; h.record_len = a->record_len; h.x = a->xres;
-      h.w1[0] = a->head_w1[0]; h.w1[1] = a->head_w1[1]; h.b1 = a->head_b1;
-      h.w2[0] = a->head_w2[0]; h.w2[1] = a->head_w2[1]; h.b2 = a->head_b2; h.out = a->out;
+      HMVIT_CHECK_ARG(a->head_w1h[0] && a->head_w1h[1] && a->head_w2h[0] && a->head_w2h[1], "fusion_forward: fp16 head weights missing");
+      h.w1[0] = a->head_w1h[0]; h.w1[1] = a->head_w1h[1]; h.b1 = a->head_b1;
+      h.w2[0] = a->head_w2h[0]; h.w2[1] = a->head_w2h[1]; h.b2 = a->head_b2; h.out = a->out;
       int rc = hmvit_ffn_head(&h, stream); if (rc) return rc;
     }
   }

@@ -1,7 +1,10 @@
 // Fused post-attention chain for one 128-token tile (sm_100a, persistent, warp-specialised):
 //
 //   x'  = x + O W_a^T + b_a                       (typed output projection + residual, bf16 operands)
-//   x'' = x' + W_2 gelu(W_1 LN'_t(x') + b_1) + b_2   (typed pre-norm FFN + residual, tf32 operands)
+//   x'' = x' + W_2 gelu(W_1 LN'_t(x') + b_1) + b_2   (typed pre-norm FFN + residual, fp16 operands: the same 11-bit
+//                                                      significand as tf32 at twice the MMA rate and half the operand
+//                                                      bytes; conversions saturate at +-65504 -- LN outputs are
+//                                                      bounded by 16, measured parity identical to tf32)
 //
 // Replaces HeteroAttention.to_out (hetero_fusion.py:142-152), the residual (:399 / :442) and
 // HeteroPreNormResidual(HeteroFeedForward) (base_transformer.py:129-136, 180-192): five reference ops
@@ -10,12 +13,12 @@
 // Data flow per tile (TMEM: D1 = columns 0..255, D2 = columns 256..511):
 //   P1  O tile (TMA, bf16) x W_a (TMA ring)            -> D1                       tcgen05 kind::f16
 //   E1  D1 + b_a + x (channel-major fp32)              -> x' written back to D1, LN statistics
-//   P2  LN'(x') as tf32 32-channel K-chunks (smem ring) x W_1 -> D2                tcgen05 kind::tf32
-//   P3  gelu(D2 + b_1) as tf32 K-chunks (same ring) x W_2     -> accumulated ONTO x' in D1
+//   P2  LN'(x') as fp16 64-channel K-chunks (smem ring) x W_1 -> D2                tcgen05 kind::f16
+//   P3  gelu(D2 + b_1) as fp16 K-chunks (same ring) x W_2     -> accumulated ONTO x' in D1
 //   E2  D1 + b_2                                       -> x'' stored channel-major (+ LN statistics)
 // Warp roles (18 warps): warps 0-15 transform / epilogue in 4 groups of 4 warps -- thread == token row
 // == TMEM lane (lane quarter = warp % 4), group g owns columns [64g, 64g+64) in E1 / E2 and the
-// K-chunks {g, g+4} in the P2 / P3 feeds, so four chunks are produced concurrently and every SM
+// K-chunk g in the P2 / P3 feeds, so four chunks are produced concurrently and every SM
 // sub-partition has four transform warps to hide TMEM / global latency; warp 16 TMA producer;
 // warp 17 MMA issuer (+ TMEM allocator).
 #pragma once
@@ -61,7 +64,7 @@ struct ChainParams {
 struct ChainMaps {             // TMA tensor maps
   CUtensorMap o;               // attention output rows bf16 [B*L*N][256], box 64 x 128
   CUtensorMap wa[2];           // bf16 [256][256], box 64 x 256
-  CUtensorMap w1[2];           // fp32 [256][256], box 32 x 256
+  CUtensorMap w1[2];           // fp16 [256][256], box 64 x 256
   CUtensorMap w2[2];
 };
 
@@ -71,7 +74,7 @@ struct ChainCfg {
   static constexpr int WSTAGE = 32768;                // weight stage: 256 output channels x 128 B of K
   // NF must be 4: ring stage g belongs to transform group g (single producer per stage, generations in
   // program order -- an mbarrier parity wait cannot tell generation k from k - 2).
-  static constexpr int NF = 4;                        // tf32 A-chunk ring stages
+  static constexpr int NF = 4;                        // fp16 A-chunk ring stages (64 channels each)
   static constexpr int NS = 2;                        // weight ring stages (32 KB each)
   static constexpr int AO_BYTES = 4 * CHUNK;          // O tile, bf16
   static constexpr int PART_BYTES = 4 * 128 * 8;      // per-group partial LN statistics
@@ -222,25 +225,24 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         rstd = st.y; nmr = -st.x * st.y;
       }
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 2);
-      // ---- P2 feed: LN'(x') -> tf32 K-chunks kc = 2gq, 2gq + 1 (this group's own columns, from registers) ----
+      // ---- P2 feed: LN'(x') -> fp16 K-chunk gq (this group's own 64 columns, from registers) ----
       const bool affine = p.ln_gamma != nullptr;
-      const float* gam = affine ? p.ln_gamma + type * kC : nullptr;
-      const float* bet = affine ? p.ln_beta + type * kC : nullptr;
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        const int kc = 2 * gq + kk;
-        // ring stage gq belongs to this group (single producer): 4 generations per tile (P2: 2, P3: 2)
-        const uint32_t fs = gq, ph = (ti * 4 + kk) & 1u;
+      const float* gam = affine ? p.ln_gamma + type * kC + c0 : nullptr;
+      const float* bet = affine ? p.ln_beta + type * kC + c0 : nullptr;
+      {
+        // ring stage gq belongs to this group (single producer): 2 generations per tile (P2, P3)
+        const uint32_t fs = gq;
         uint32_t r[32];
         if (affine) {
 #pragma unroll
           for (int k = 0; k < 32; ++k)
-            r[k] = __float_as_uint(tf32_rn(fmaf(rv[kk * 32 + k], rstd, nmr) * __ldg(gam + kc * 32 + k) + __ldg(bet + kc * 32 + k)));
+            r[k] = pack_f16x2(fmaf(rv[2 * k], rstd, nmr) * __ldg(gam + 2 * k) + __ldg(bet + 2 * k),
+                              fmaf(rv[2 * k + 1], rstd, nmr) * __ldg(gam + 2 * k + 1) + __ldg(bet + 2 * k + 1));
         } else {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(tf32_rn(fmaf(rv[kk * 32 + k], rstd, nmr)));
+          for (int k = 0; k < 32; ++k) r[k] = pack_f16x2(fmaf(rv[2 * k], rstd, nmr), fmaf(rv[2 * k + 1], rstd, nmr));
         }
-        mbar_wait(&f_empty[fs], ph ^ 1u);
+        mbar_wait(&f_empty[fs], 1u);                 // generation 2 ti: parity 0, wait on the previous one
         uint8_t* dstF = sF + fs * Cfg::CHUNK;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -250,26 +252,30 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         mbar_arrive(&f_full[fs]);
       }
       prefetch_resid_l2(t_next);
-      // ---- P3 feed: gelu(D2 + b_1) -> tf32 K-chunks kc = 2gq, 2gq + 1 ----
+      // ---- P3 feed: gelu(D2 + b_1) -> fp16 K-chunk gq ----
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 3);
       mbar_wait(d2_full, ti & 1);
       tc_fence_after();
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 4);
-      const float* b1 = sBias + 2 * kC + type * kC;
-#pragma unroll 1
-      for (int kk = 0; kk < 2; ++kk) {
-        const int kc = 2 * gq + kk;
-        const uint32_t fs = gq, ph = (ti * 4 + 2 + kk) & 1u;
-        uint32_t r[32];
-        tmem_ld32(D2 + lane_base + kc * 32, r);
-        tmem_ld_wait();
+      const float* b1 = sBias + 2 * kC + type * kC + c0;
+      {
+        const uint32_t fs = gq;
+        uint32_t h2[32];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) r[k] = __float_as_uint(tf32_rn(gelu_erf_fast(__uint_as_float(r[k]) + b1[kc * 32 + k])));
-        mbar_wait(&f_empty[fs], ph ^ 1u);
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r[32];
+          tmem_ld32(D2 + lane_base + c0 + hf * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            h2[hf * 16 + k] = pack_f16x2(gelu_erf_fast(__uint_as_float(r[2 * k]) + b1[hf * 32 + 2 * k]),
+                                         gelu_erf_fast(__uint_as_float(r[2 * k + 1]) + b1[hf * 32 + 2 * k + 1]));
+        }
+        mbar_wait(&f_empty[fs], 0u);                 // generation 2 ti + 1: the P2 chunk of this tile has been consumed
         uint8_t* dstF = sF + fs * Cfg::CHUNK;
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<uint4*>(dstF + sw128_offset(row, u)) = make_uint4(r[u * 4], r[u * 4 + 1], r[u * 4 + 2], r[u * 4 + 3]);
+          *reinterpret_cast<uint4*>(dstF + sw128_offset(row, u)) = make_uint4(h2[u * 4], h2[u * 4 + 1], h2[u * 4 + 2], h2[u * 4 + 3]);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&f_full[fs]);
@@ -335,8 +341,8 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
           ++itw;
         };
         if constexpr (!kHead) for (int kc = 0; kc < 4; ++kc) wstage(&maps.wa[type], kc * 64);
-        for (int j = 0; j < 8; ++j) wstage(&maps.w1[type], (2 * (j & 3) + (j >> 2)) * 32);   // same order as the MMA issuer
-        for (int j = 0; j < 8; ++j) wstage(&maps.w2[type], (2 * (j & 3) + (j >> 2)) * 32);
+        for (int j = 0; j < 4; ++j) wstage(&maps.w1[type], j * 64);   // K-chunk j == transform group j, same order as the MMA issuer
+        for (int j = 0; j < 4; ++j) wstage(&maps.w2[type], j * 64);
         ++ti;
       }
     }
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
     // ============================ MMA issuer ============================
     if (lane == 0) {
       constexpr uint32_t idesc_bf16 = umma_idesc(1u, 128, 256);
-      constexpr uint32_t idesc_tf32 = umma_idesc(2u, 128, 256);
+      constexpr uint32_t idesc_f16 = umma_idesc(0u, 128, 256);     // fp16 operands, fp32 accumulate
       const uint32_t o_base = smem_u32(sO), f_base = smem_u32(sF), w_base = smem_u32(sW);
       uint32_t ti = 0, itw = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -373,13 +379,11 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
           umma_commit(d1_full);
         }
         CHAIN_TS(1, ti, 3);
-        // P2: D2 = LN'(x') W_1^T      P3: D1 += gelu(.) W_2^T     (8 stages of 32 K-columns each)
+        // P2: D2 = LN'(x') W_1^T      P3: D1 += gelu(.) W_2^T     (4 stages of 64 K-columns each)
         for (int phase = 0; phase < 2; ++phase) {
           const uint32_t dacc = phase == 0 ? D2 : D1;
-          // K-chunks are consumed first-chunk-of-every-group first (j -> group j % 4, sub-chunk j / 4 of that
-          // group), the order in which the four transform groups finish them; accumulation order is free
-          for (int j = 0; j < 8; ++j, ++itw) {
-            const uint32_t fs = j & 3, fph = (ti * 4 + phase * 2 + (j >> 2)) & 1u;
+          for (int j = 0; j < 4; ++j, ++itw) {
+            const uint32_t fs = j, fph = phase;                  // generation 2 ti + phase of ring stage j
             const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
             mbar_wait(&f_full[fs], fph);
             mbar_wait(&w_full[s], ph);
@@ -387,8 +391,8 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
             if (!(HMVIT_CHAIN_DBG & 4))
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks)
-              umma_ss<4>(dacc, umma_desc_sw128(f_base + fs * Cfg::CHUNK + ks * 32),
-                         umma_desc_sw128(w_base + s * Cfg::WSTAGE + ks * 32), idesc_tf32,
+              umma_ss<2>(dacc, umma_desc_sw128(f_base + fs * Cfg::CHUNK + ks * 32),
+                         umma_desc_sw128(w_base + s * Cfg::WSTAGE + ks * 32), idesc_f16,
                          ((phase == 1 && !kHead) || (j | ks) != 0) ? 1u : 0u);
             umma_commit(&w_empty[s]);
             umma_commit(&f_empty[fs]);

@@ -36,6 +36,12 @@ HMVIT_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// two fp32 -> packed fp16 (lo in the low half), round to nearest, saturating at +-65504 instead of overflowing to inf
+HMVIT_DEVINL uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 HMVIT_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 HMVIT_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
@@ -191,7 +197,7 @@ HMVIT_DEVINL uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, A/B K-major.
-// fmt: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
+// fmt: 0 = F16, 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
 __host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }

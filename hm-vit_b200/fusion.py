@@ -307,6 +307,9 @@ class HeteroFusionBlock(nn.Module):
             pk[f"w1_{t}"] = _tf32_round(w1 * g2[t][None, :])
             b1.append(ffd.fn.net[t][0].bias.detach().float() + w1 @ b2n[t])
             pk[f"w2_{t}"] = _tf32_round(ffd.fn.net[t][3].weight)
+            # fp16 copies for the fused chain kernel: the same 11-bit significand as tf32 at twice the MMA rate
+            pk[f"w1h_{t}"] = (w1 * g2[t][None, :]).half().contiguous()
+            pk[f"w2h_{t}"] = ffd.fn.net[t][3].weight.detach().half().contiguous()
         pk["b1"] = torch.stack(b1).contiguous()
         pk["b2"] = _stack2(lambda t: ffd.fn.net[t][3].bias.detach().float())
         return pk
@@ -353,6 +356,9 @@ class HeteroFusion(nn.Module):
             net = self.mlp_head.net
             pk = {f"w1_{t}": _tf32_round(net[t][0].weight) for t in range(2)}
             pk.update({f"w2_{t}": _tf32_round(net[t][3].weight) for t in range(2)})
+            # fp16 copies for the fused head kernel (same significand width as tf32)
+            pk.update({f"w1h_{t}": net[t][0].weight.detach().half().contiguous() for t in range(2)})
+            pk.update({f"w2h_{t}": net[t][3].weight.detach().half().contiguous() for t in range(2)})
             pk["b1"] = _stack2(lambda t: net[t][0].bias.detach().float())
             pk["b2"] = _stack2(lambda t: net[t][3].bias.detach().float())
             self._head_cache = (key, pk)
@@ -395,6 +401,8 @@ def _fill_stage(sw: "_lib.StageWeights", pk: Dict[str, torch.Tensor]):
     sw.w2[0], sw.w2[1] = pk["w2_0"].data_ptr(), pk["w2_1"].data_ptr()
     sw.b1, sw.b2 = pk["b1"].data_ptr(), pk["b2"].data_ptr()
     sw.bias_table = pk["bias_table"].data_ptr()
+    sw.w1h[0], sw.w1h[1] = pk["w1h_0"].data_ptr(), pk["w1h_1"].data_ptr()
+    sw.w2h[0], sw.w2h[1] = pk["w2h_0"].data_ptr(), pk["w2h_1"].data_ptr()
 
 
 def _run_fusion(block: HeteroFusionBlock, fusion, x, pairwise_t_matrix, mode, record_len, mask, num_iters, xres=None):
@@ -442,6 +450,8 @@ def _run_fusion(block: HeteroFusionBlock, fusion, x, pairwise_t_matrix, mode, re
         keep.append(hp)
         args.head_w1[0], args.head_w1[1] = hp["w1_0"].data_ptr(), hp["w1_1"].data_ptr()
         args.head_w2[0], args.head_w2[1] = hp["w2_0"].data_ptr(), hp["w2_1"].data_ptr()
+        args.head_w1h[0], args.head_w1h[1] = hp["w1h_0"].data_ptr(), hp["w1h_1"].data_ptr()
+        args.head_w2h[0], args.head_w2h[1] = hp["w2h_0"].data_ptr(), hp["w2h_1"].data_ptr()
         args.head_b1, args.head_b2 = hp["b1"].data_ptr(), hp["b2"].data_ptr()
         args.out = out.data_ptr()
     args.xres, args.workspace = xres.data_ptr(), ws.data_ptr()

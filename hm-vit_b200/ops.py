@@ -51,8 +51,15 @@ def rowgemm(variant, *, B, L, N, n_out, mode, record_len, a, w0, w1, bias, out, 
     return out
 
 
+def _as_half(w):
+    """The chain kernel takes fp16 feed-forward weights (same significand width as tf32).  fp16 tensors pass through
+    (the packed dicts of fusion.py / training.py carry them as w1h_* / w2h_*); fp32 ones are converted per call."""
+    return w if w.dtype == torch.float16 else w.detach().half().contiguous()
+
+
 def out_ffn_chain(*, B, L, N, mode, record_len, o, resid, out, wa0, wa1, ba, w1_0, w1_1, b1, w2_0, w2_1, b2,
                   ln_gamma=None, ln_beta=None, ego_only=False, ln_eps=1e-5, stats_out=None):
+    w1_0, w1_1, w2_0, w2_1 = _as_half(w1_0), _as_half(w1_1), _as_half(w2_0), _as_half(w2_1)
     args = _lib.ChainArgs()
     args.B, args.L, args.N = B, L, N
     args.mode, args.record_len = mode.data_ptr(), record_len.data_ptr()
@@ -72,6 +79,7 @@ def out_ffn_chain(*, B, L, N, mode, record_len, o, resid, out, wa0, wa1, ba, w1_
 def ffn_head(*, B, L, N, mode, record_len, x, w1_0, w1_1, b1, w2_0, w2_1, b2, out):
     """Typed feed-forward head on slot 0 of every scene (HeteroFusion.mlp_head,
     bevformer_point_pillar_hetero.py:46-48): out[B,256,N] = W2 gelu(W1 x + b1) + b2."""
+    w1_0, w1_1, w2_0, w2_1 = _as_half(w1_0), _as_half(w1_1), _as_half(w2_0), _as_half(w2_1)
     args = _lib.HeadArgs()
     args.B, args.L, args.N = B, L, N
     args.mode, args.record_len = mode.data_ptr(), record_len.data_ptr()

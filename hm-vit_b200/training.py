@@ -116,6 +116,9 @@ def kernel_pack_stage(F: Dict[str, torch.Tensor], rows_dtype) -> Dict[str, torch
         pk[f"wa{t}"] = _lowp(F["wa"][t], rows_dtype)
         pk[f"w1_{t}"] = _tf32(F["w1"][t], exact)
         pk[f"w2_{t}"] = _tf32(F["w2"][t], exact)
+        # the fused chain kernel takes fp16 feed-forward weights (same significand width as tf32); exact on the CPU emulation
+        pk[f"w1h_{t}"] = F["w1"][t].detach().contiguous() if exact else F["w1"][t].detach().half().contiguous()
+        pk[f"w2h_{t}"] = F["w2"][t].detach().contiguous() if exact else F["w2"][t].detach().half().contiguous()
         pk[f"waT{t}"] = _tf32(F["wa"][t].t(), exact)
         pk[f"w1T{t}"] = _tf32(F["w1"][t].t(), exact)
         pk[f"w2T{t}"] = _tf32(F["w2"][t].t(), exact)
@@ -174,7 +177,7 @@ def forward_train(ops, geo, x, packs, head_pack, num_iters, skip_dead):
                        out=att, ego_only=dead, lse=lse)
         xout = torch.zeros_like(xin)
         ops.out_ffn_chain(o=att, resid=xin, out=xout, wa0=pk["wa0"], wa1=pk["wa1"], ba=pk["ba"],
-                          w1_0=pk["w1_0"], w1_1=pk["w1_1"], b1=pk["b1"], w2_0=pk["w2_0"], w2_1=pk["w2_1"], b2=pk["b2"],
+                          w1_0=pk["w1h_0"], w1_1=pk["w1h_1"], b1=pk["b1"], w2_0=pk["w2h_0"], w2_1=pk["w2h_1"], b2=pk["b2"],
                           ego_only=dead, **common)
         sv.qkv.append(qkv); sv.att.append(att); sv.lse.append(lse); sv.dead.append(dead); sv.xs.append(xout)
     out = None

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMVIT_ABI_VERSION 3
+#define HMVIT_ABI_VERSION 4
 
 /* error codes */
 #define HMVIT_OK 0
@@ -101,9 +101,9 @@ typedef struct {
   const float* ln_gamma;      /* [2][256], or NULL when the affine is folded into w1 / b1 */
   const float* ln_beta;       /* [2][256] or NULL */
   float ln_eps;
-  const void* w1[2];          /* fp32 (tf32) [256][256] */
+  const void* w1[2];          /* fp16 [256][256] (same 11-bit significand as tf32, twice the MMA rate) */
   const float* b1;            /* [2][256] */
-  const void* w2[2];          /* fp32 (tf32) [256][256] */
+  const void* w2[2];          /* fp16 [256][256] */
   const float* b2;            /* [2][256] */
   float* stats_out;           /* optional [B*L][N][2]: (mean, rstd) of every output row, the LayerNorm statistics
                                  the next stage's QKV projection needs; NULL = not written */
@@ -116,15 +116,15 @@ int hmvit_out_ffn_chain(const HmvitChainArgs* args, void* stream);
  *   opencood/models/bevformer_point_pillar_hetero.py:36, 46-48
  *   (HeteroFeedForward, opencood/models/base_transformer.py:180-192: Linear - GELU(erf) - Linear per agent type,
  *    no LayerNorm, no residual).
- * out[b] = W_2 gelu(W_1 x[b, slot 0] + b_1) + b_2, one launch of the chain kernel's head instance (tf32 operands). */
+ * out[b] = W_2 gelu(W_1 x[b, slot 0] + b_1) + b_2, one launch of the chain kernel's head instance (fp16 operands, fp32 accumulate). */
 typedef struct {
   int32_t B, L, N;
   const int32_t* mode;
   const int32_t* record_len;
   const float* x;             /* fp32 cm [B*L][256][N]; only slot 0 of every scene is read */
-  const void* w1[2];          /* fp32 (tf32) [256][256] per type */
+  const void* w1[2];          /* fp16 [256][256] per type */
   const float* b1;            /* [2][256] */
-  const void* w2[2];          /* fp32 (tf32) [256][256] per type */
+  const void* w2[2];          /* fp16 [256][256] per type */
   const float* b2;            /* [2][256] */
   float* out;                 /* fp32 cm [B][256][N] */
 } HmvitHeadArgs;
@@ -193,6 +193,8 @@ typedef struct {
   const void* w2[2];          /* fp32 (tf32) [256][256] */
   const float* b2;            /* [2][256] */
   const float* bias_table;    /* [225][8] */
+  const void* w1h[2];         /* fp16 [256][256] copies of w1 / w2 for the fused chain kernel (w1 / w2 serve the unfused row-GEMMs) */
+  const void* w2h[2];
 } HmvitStageWeights;
 
 typedef struct {
@@ -216,6 +218,8 @@ typedef struct {
   float* xres;                /* fp32 cm [B*L][256][N]: residual stream / block output (valid slots) */
   void* workspace;            /* hmvit_fusion_workspace_bytes() bytes */
   float* out;                 /* fp32 [B][256][N] (head == 1) */
+  const void* head_w1h[2];    /* fp16 [256][256] copies of head_w1 / head_w2 for the fused head kernel */
+  const void* head_w2h[2];
 } HmvitFusionArgs;
 
 size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W);
