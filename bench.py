@@ -424,7 +424,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 (projections, attention) + tf32 (FFN), fp32 accumulate and residual stream",
+        "dtype": "bf16 (projections, attention) + fp16 (FFN), fp32 accumulate and residual stream",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "scenes_per_gpu_per_step": Bq, "agents": L, "bev": [C, H, W],
                    "l2": "inputs per step (346 MB fp32 features + 3.5 GB workspace) exceed the 126 MB L2; no explicit flush",

@@ -521,7 +521,27 @@ def check_ragged_batch():
     return res
 
 
-CHECKS.update({"cuda_graph": check_cuda_graph, "ragged_batch": check_ragged_batch})
+def check_partial_tile():
+    """A map whose token count is not a multiple of the 128-token GEMM tile (24 x 24 = 576 = 4.5 tiles): the last tile
+    of every agent is half empty in the QKV / chain / head kernels (clamped loads, clipped stores); against the oracle."""
+    cfg, P, net = _mk_module(1)
+    B, L, H, W = 2, 3, 24, 24
+    x, T, md, rl, mask = _scene(B, L, H, W, [3, 2], seed=33, mode=[[1, 0, 1], [0, 1, 0]], tx=8, ty=8)
+    with torch.no_grad():
+        y = net(x.to(DEV), T.to(DEV), md.to(DEV), rl.to(DEV), mask.to(DEV)).cpu()
+        yb = net.hetero_fusion_block(x.to(DEV), T.to(DEV), md.to(DEV), rl.to(DEV), mask.to(DEV)).cpu()
+    ref = O.hetero_fusion(x, T, md, rl, mask, P, cfg)
+    refb = O.hetero_fusion_block(x, T, md, rl, mask, P, cfg["hetero_fusion_block"]) if hasattr(O, "hetero_fusion_block") else None
+    res = {"rel_l2_vs_oracle": rel_l2(y, ref), "finite": bool(torch.isfinite(y).all())}
+    if refb is not None:
+        errs = [rel_l2(yb[b, l], refb[b, l]) for b in range(B) for l in range(int(rl[b]))]
+        res["block_worst_rel_l2"] = max(errs)
+        assert res["block_worst_rel_l2"] < 1e-3, res
+    assert res["finite"] and res["rel_l2_vs_oracle"] < 1e-3, res
+    return res
+
+
+CHECKS.update({"cuda_graph": check_cuda_graph, "ragged_batch": check_ragged_batch, "partial_tile": check_partial_tile})
 # (attn_split_vs_single is registered next to the backward checks below: it uses tests/emul_ops.py)
 
 
