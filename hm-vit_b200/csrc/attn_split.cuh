@@ -174,14 +174,20 @@ __global__ void __launch_bounds__(kCompactThreads, 4) warp_compact_kernel(const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared memory: Q | K buffer 0 | K buffer 1 | V | bias table | 3 mbarriers  (68 KB -> 3 CTAs per SM)
-constexpr int kDenseSmem = 4 * kTileBytes + kHG * kBiasStride * 4 + 32;
+// shared memory: Q | K buffer 0 | K buffer 1 | V buffer 0 | V buffer 1 | bias table | 4 mbarriers  (84 KB)
+constexpr int kDenseSmem = 5 * kTileBytes + kHG * kBiasStride * 4 + 32;
 #ifndef HMVIT_DENSE_WARPS
 #define HMVIT_DENSE_WARPS 4                                // 4 query row blocks x (warps / 4) head sets; measured on B200
                                                            // (config 2): 4 warps x 3 CTAs/SM 0.48-0.53 ms, 8 x 2 0.50-0.55 ms
 #endif
+#ifndef HMVIT_DENSE_HEADWARP
+#define HMVIT_DENSE_HEADWARP 1                             // 1: warp == head (all 64 query rows), K / V fragments read from shared
+                                                           // memory once per tile instead of once per 16-row block (4 warps only):
+                                                           // 46 % fewer shared-memory wavefronts, 255 registers, 2 CTAs / SM;
+                                                           // measured 0.353 vs 0.365 ms (0: warp == 16-row block x 4 heads, 3 CTAs / SM)
+#endif
 #ifndef HMVIT_DENSE_CTAS
-#define HMVIT_DENSE_CTAS 3                                 // resident CTAs per SM the register budget is sized for
+#define HMVIT_DENSE_CTAS (HMVIT_DENSE_HEADWARP ? 2 : 3)                                 // resident CTAs per SM the register budget is sized for
 #endif
 constexpr int kDenseWarps = HMVIT_DENSE_WARPS;
 constexpr int kDenseThreads = kDenseWarps * 32;
@@ -189,6 +195,7 @@ constexpr int kHPW = kHG / (kDenseWarps / 4);              // heads per warp
 constexpr int kStageIt = 8 / (kDenseWarps / 4);            // token pairs a warp stages (Q, self tile, output)
 constexpr int kBiasIt = (225 * kHG + kDenseThreads - 1) / kDenseThreads;
 static_assert(kDenseWarps == 4 || kDenseWarps == 8 || kDenseWarps == 16, "dense attention: 4, 8 or 16 warps");
+static_assert(!HMVIT_DENSE_HEADWARP || kDenseWarps == 4, "warp == head needs 4 warps");
 
 HMVIT_DEVINL void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -196,8 +203,7 @@ HMVIT_DEVINL void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, 
 }
 
 // Key tiles are consumed in order [self tile (when the ego's own transform is the identity)] [compacted tiles 0..].
-// K is double buffered (the next tile's keys arrive during this tile's work); V is single buffered: its copy is
-// issued when the previous tile is finished and lands under the QK^T + softmax of the first head.
+// K and V are double buffered: the next tile's keys and values arrive during this tile's work.
 __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_kernel(const SplitParams sp) {
   const AttnParams& p = sp.a;
   const int a = blockIdx.y;
@@ -217,8 +223,8 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTileBytes;                                            // two buffers
   uint8_t* sV = smem + 3 * kTileBytes;
-  float* sBias = reinterpret_cast<float*>(smem + 4 * kTileBytes);             // [4][kBiasStride], log2 domain
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kHG * kBiasStride);    // K buffer 0, K buffer 1, V
+  float* sBias = reinterpret_cast<float*>(smem + 5 * kTileBytes);             // [4][kBiasStride], log2 domain
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + kHG * kBiasStride);    // K buffer 0, K buffer 1, V buffer 0, V buffer 1
 
   const size_t ag = static_cast<size_t>(a) * G + grp;
   const int nv = sp.nvis[ag];
@@ -230,15 +236,13 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
   const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
 
   if (threadIdx.x == 0) {
-    mbar_init(bars + 0, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1);
+    mbar_init(bars + 0, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1);
     fence_mbar_init();
-    if (ntiles > 0) {                                          // compacted tile 0: keys now, values too unless the self tile uses sV first
+    if (ntiles > 0) {                                          // compacted tile 0 -> buffers `self` (the self tile, if any, owns buffers 0)
       mbar_arrive_expect_tx(bars + self, kBlobBytes);
       bulk_load(sK_u + self * kTileBytes, kblob, kBlobBytes, bars + self);
-      if (!self) {
-        mbar_arrive_expect_tx(bars + 2, kBlobBytes);
-        bulk_load(sV_u, vblob, kBlobBytes, bars + 2);
-      }
+      mbar_arrive_expect_tx(bars + 2 + self, kBlobBytes);
+      bulk_load(sV_u + self * kTileBytes, vblob, kBlobBytes, bars + 2 + self);
     }
   }
 
@@ -332,16 +336,115 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
         const uint32_t s4 = s01 | (s23 << 16);                                             // 4 slot bytes
         koff[q] = ((s4 >> 3) & 0x07070707u) * 15u + (s4 & 0x07070707u);                    // per byte, <= 112: no carry
       }
-      if (threadIdx.x == 0 && tile + 1 < ntiles) {             // next tile's keys into the other buffer
+      if (threadIdx.x == 0 && tile + 1 < ntiles) {             // next tile's keys and values into the other buffers
         fence_proxy_async_smem();
         mbar_arrive_expect_tx(bars + (kb ^ 1), kBlobBytes);
         bulk_load(sK_u + (kb ^ 1) * kTileBytes, kblob + static_cast<size_t>(tile + 1) * 2 * kBlobBytes, kBlobBytes, bars + (kb ^ 1));
+        mbar_arrive_expect_tx(bars + 2 + (kb ^ 1), kBlobBytes);
+        bulk_load(sV_u + (kb ^ 1) * kTileBytes, vblob + static_cast<size_t>(tile + 1) * 2 * kBlobBytes, kBlobBytes, bars + 2 + (kb ^ 1));
       }
       mbar_wait(bars + kb, (phases >> kb) & 1u); phases ^= 1u << kb;
     }
     const int nval = tile < 0 ? kS : min(kS, nv - tile * kS);
-    const uint32_t sKb = sK_u + kb * kTileBytes;
+    const uint32_t sKb = sK_u + kb * kTileBytes, sVb = sV_u + kb * kTileBytes;
 
+#if HMVIT_DENSE_HEADWARP
+    {
+      // warp == head hd of the head group; hh runs over the four 16-row query blocks.  The K fragments of the tile are
+      // loaded once (before the loop), the V fragments once (after the first block's QK^T, when the values have landed).
+      const int hd = warp;
+      uint32_t kbA[4][4], kbB[4][4], vbAll[4][2][4];
+      {
+        const int krow = (lane & 7) + (lane >> 4) * 8;
+        const int kunit = hd * 4 + ((lane >> 3) & 1);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          ldsm_x4(sKb + tile_off(np * 16 + krow, kunit), kbA[np][0], kbA[np][1], kbA[np][2], kbA[np][3]);
+          ldsm_x4(sKb + tile_off(np * 16 + krow, kunit + 2), kbB[np][0], kbB[np][1], kbB[np][2], kbB[np][3]);
+        }
+      }
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        const float* bh = sBias + hd * kBiasStride + (2 * hh + 7) * 15 + (g + 7);
+        float sacc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const uint32_t kf = koff[nt >> 1] >> ((nt & 1) * 16);
+          const int k0 = kf & 0xff, k1 = (kf >> 8) & 0xff;
+          sacc[nt][0] = bh[-k0];      sacc[nt][1] = bh[-k1];
+          sacc[nt][2] = bh[15 - k0];  sacc[nt][3] = bh[15 - k1];
+        }
+        {
+          uint32_t qa[2][4];
+          const int qrow = hh * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+          ldsm_x4(sQ_u + tile_off(qrow, hd * 4 + (lane >> 4)), qa[0][0], qa[0][1], qa[0][2], qa[0][3]);
+          ldsm_x4(sQ_u + tile_off(qrow, hd * 4 + 2 + (lane >> 4)), qa[1][0], qa[1][1], qa[1][2], qa[1][3]);
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            mma_bf16(sacc[np * 2], qa[0][0], qa[0][1], qa[0][2], qa[0][3], kbA[np][0], kbA[np][1]);
+            mma_bf16(sacc[np * 2 + 1], qa[0][0], qa[0][1], qa[0][2], qa[0][3], kbA[np][2], kbA[np][3]);
+          }
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            mma_bf16(sacc[np * 2], qa[1][0], qa[1][1], qa[1][2], qa[1][3], kbB[np][0], kbB[np][1]);
+            mma_bf16(sacc[np * 2 + 1], qa[1][0], qa[1][1], qa[1][2], qa[1][3], kbB[np][2], kbB[np][3]);
+          }
+        }
+        if (nval < kS) {                                          // tail of the last tile
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              if (nt * 8 + 2 * t + e >= nval) { sacc[nt][e] = -INFINITY; sacc[nt][2 + e] = -INFINITY; }
+            }
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+          mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(mrow[hh][0], mx0), mn1 = fmaxf(mrow[hh][1], mx1);
+        const float mu0 = (mn0 == -INFINITY) ? 0.f : mn0, mu1 = (mn1 == -INFINITY) ? 0.f : mn1;
+        const float al0 = ex2(mrow[hh][0] - mu0), al1 = ex2(mrow[hh][1] - mu1);
+        mrow[hh][0] = mn0; mrow[hh][1] = mn1;
+        uint32_t pa[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float p0 = ex2(sacc[nt][0] - mu0), p1 = ex2(sacc[nt][1] - mu0);
+          const float p2 = ex2(sacc[nt][2] - mu1), p3 = ex2(sacc[nt][3] - mu1);
+          pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
+          pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+        float lacc[4] = {lrow[hh][0] * al0, 0.f, lrow[hh][1] * al1, 0.f};
+#pragma unroll
+        for (int n = 0; n < 4; ++n) { o[hh][n][0] *= al0; o[hh][n][1] *= al0; o[hh][n][2] *= al1; o[hh][n][3] *= al1; }
+        if (hh == 0) {
+          if (tile >= 0) { mbar_wait(bars + 2 + kb, (phases >> (2 + kb)) & 1u); phases ^= 4u << kb; }     // this tile's values have landed
+          const int vrow = (lane & 7) + ((lane >> 3) & 1) * 8;
+          const int vunit = hd * 4 + (lane >> 4);
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+            for (int np = 0; np < 2; ++np)
+              ldsm_x4_t(sVb + tile_off(kc * 16 + vrow, vunit + np * 2), vbAll[kc][np][0], vbAll[kc][np][1], vbAll[kc][np][2], vbAll[kc][np][3]);
+        }
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+          mma_bf16(lacc, pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], 0x3F803F80u, 0x3F803F80u);
+#pragma unroll
+          for (int np = 0; np < 2; ++np) {
+            mma_bf16(o[hh][np * 2], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], vbAll[kc][np][0], vbAll[kc][np][1]);
+            mma_bf16(o[hh][np * 2 + 1], pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], vbAll[kc][np][2], vbAll[kc][np][3]);
+          }
+        }
+        lrow[hh][0] = lacc[0]; lrow[hh][1] = lacc[2];
+      }
+    }
+#else
 #pragma unroll
     for (int hh = 0; hh < kHPW; ++hh) {
       const int hd = h0 + hh;                                   // head within the head group
@@ -413,20 +516,20 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
       float lacc[4] = {lrow[hh][0] * al0, 0.f, lrow[hh][1] * al1, 0.f};
 #pragma unroll
       for (int n = 0; n < 4; ++n) { o[hh][n][0] *= al0; o[hh][n][1] *= al0; o[hh][n][2] *= al1; o[hh][n][3] *= al1; }
-      if (hh == 0 && tile >= 0) { mbar_wait(bars + 2, (phases >> 2) & 1u); phases ^= 4u; }     // this tile's values have landed
+      if (hh == 0 && tile >= 0) { mbar_wait(bars + 2 + kb, (phases >> (2 + kb)) & 1u); phases ^= 4u << kb; }     // this tile's values have landed
       {
         uint32_t vb[2][2][4];                                    // [buffer][dim n-tile pair][fragment]
         const int vrow = (lane & 7) + ((lane >> 3) & 1) * 8;
         const int vunit = hd * 4 + (lane >> 4);
 #pragma unroll
-        for (int np = 0; np < 2; ++np) ldsm_x4_t(sV_u + tile_off(vrow, vunit + np * 2), vb[0][np][0], vb[0][np][1], vb[0][np][2], vb[0][np][3]);
+        for (int np = 0; np < 2; ++np) ldsm_x4_t(sVb + tile_off(vrow, vunit + np * 2), vb[0][np][0], vb[0][np][1], vb[0][np][2], vb[0][np][3]);
 #pragma unroll
         for (int kc = 0; kc < 4; ++kc) {
           const int cur = kc & 1;
           if (kc < 3) {
 #pragma unroll
             for (int np = 0; np < 2; ++np)
-              ldsm_x4_t(sV_u + tile_off((kc + 1) * 16 + vrow, vunit + np * 2), vb[cur ^ 1][np][0], vb[cur ^ 1][np][1], vb[cur ^ 1][np][2], vb[cur ^ 1][np][3]);
+              ldsm_x4_t(sVb + tile_off((kc + 1) * 16 + vrow, vunit + np * 2), vb[cur ^ 1][np][0], vb[cur ^ 1][np][1], vb[cur ^ 1][np][2], vb[cur ^ 1][np][3]);
           }
           mma_bf16(lacc, pa[kc][0], pa[kc][1], pa[kc][2], pa[kc][3], 0x3F803F80u, 0x3F803F80u);
 #pragma unroll
@@ -438,22 +541,26 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
       }
       lrow[hh][0] = lacc[0]; lrow[hh][1] = lacc[2];
     }
-    __syncthreads();                                           // every warp is done with this tile's K buffer and with sV
-    if (threadIdx.x == 0 && tile + 1 < ntiles) {               // next tile's values
-      fence_proxy_async_smem();
-      mbar_arrive_expect_tx(bars + 2, kBlobBytes);
-      bulk_load(sV_u, vblob + static_cast<size_t>(tile + 1) * 2 * kBlobBytes, kBlobBytes, bars + 2);
-    }
+#endif
+    __syncthreads();                                           // every warp is done with this tile's K and V buffers
   }
 
   // ---- training: save the softmax statistics (log2 domain: running max + log2 of the denominator) ----
   if (p.lse != nullptr && t == 0) {
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
+#if HMVIT_DENSE_HEADWARP
+#pragma unroll
+      for (int hh = 0; hh < 4; ++hh) {
+        int r, c; group_token(p.kind, gy, gx, hh * 16 + g + e * 8, p.H, p.W, r, c);
+        p.lse[(static_cast<size_t>(a) * N + r * p.W + c) * kHeads + hgc * kHG + warp] = lrow[hh][e] > 0.f ? mrow[hh][e] + log2f(lrow[hh][e]) : INFINITY;
+      }
+#else
       int r, c; group_token(p.kind, gy, gx, rb * 16 + g + e * 8, p.H, p.W, r, c);
       float* dst = p.lse + (static_cast<size_t>(a) * N + r * p.W + c) * kHeads + hgc * kHG + h0;
 #pragma unroll
       for (int hh = 0; hh < kHPW; ++hh) dst[hh] = lrow[hh][e] > 0.f ? mrow[hh][e] + log2f(lrow[hh][e]) : INFINITY;
+#endif
     }
   }
   // ---- normalise, stage in smem (K buffer 0: no copy is pending), coalesced store ----
@@ -463,8 +570,13 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
     const float il1 = lrow[hh][1] > 0.f ? 1.0f / lrow[hh][1] : 0.f;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
+#if HMVIT_DENSE_HEADWARP
+      const int col = warp * kDh + n * 8 + 2 * t;
+      const int r0 = hh * 16 + g, r1 = r0 + 8;
+#else
       const int col = (h0 + hh) * kDh + n * 8 + 2 * t;
       const int r0 = rb * 16 + g, r1 = r0 + 8;
+#endif
       *reinterpret_cast<uint32_t*>(sK + tile_off(r0, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[hh][n][0] * il0, o[hh][n][1] * il0);
       *reinterpret_cast<uint32_t*>(sK + tile_off(r1, col >> 3) + (col & 7) * 2) = pack_bf16x2(o[hh][n][2] * il1, o[hh][n][3] * il1);
     }
