@@ -315,6 +315,15 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
   const int bias_q = (2 * rb + 7) * 15 + (g + 7);
   __syncthreads();                                             // Q / bias / self tile staged, barriers initialised
 
+  // key slots of this thread's 16 columns of a compacted tile (keys nt*8 + 2t + e), requested one tile ahead
+  uint32_t slot_pf[4] = {0, 0, 0, 0};
+  auto load_slots = [&](int tile_) {
+    const uint16_t* sl = reinterpret_cast<const uint16_t*>(slots + tile_ * kS) + t;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      slot_pf[q] = __ldg(sl + (2 * q) * 4) | (static_cast<uint32_t>(__ldg(sl + (2 * q + 1) * 4)) << 16);   // key pairs nt = 2q, 2q+1
+  };
+  if (ntiles > 0) load_slots(0);
   uint32_t phases = 0;                                         // bit n: parity the next wait on barrier n expects
   const int nvt = self + ntiles;
   for (int vt = 0; vt < nvt; ++vt) {
@@ -329,13 +338,12 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
         koff[q] = k00 | ((k00 + 1) << 8) | (k10 << 16) | ((k10 + 1) << 24);
       }
     } else {
-      const uint16_t* sl = reinterpret_cast<const uint16_t*>(slots + tile * kS) + t;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const uint32_t s01 = __ldg(sl + (2 * q) * 4), s23 = __ldg(sl + (2 * q + 1) * 4);   // slots of key pairs nt = 2q, 2q+1
-        const uint32_t s4 = s01 | (s23 << 16);                                             // 4 slot bytes
+        const uint32_t s4 = slot_pf[q];                                                    // 4 slot bytes (prefetched one tile ahead)
         koff[q] = ((s4 >> 3) & 0x07070707u) * 15u + (s4 & 0x07070707u);                    // per byte, <= 112: no carry
       }
+      if (tile + 1 < ntiles) load_slots(tile + 1);             // the next tile's slots: a global load per tile stalled every warp here
       if (threadIdx.x == 0 && tile + 1 < ntiles) {             // next tile's keys and values into the other buffers
         fence_proxy_async_smem();
         mbar_arrive_expect_tx(bars + (kb ^ 1), kBlobBytes);
