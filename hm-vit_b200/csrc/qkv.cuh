@@ -78,12 +78,8 @@ struct QkvCfg {
 #define HMVIT_QKV_PW 8
 #endif
   static constexpr int PROD_WARPS = HMVIT_QKV_PW;      // 4: one thread per token row; 8: two threads per row (128 channels each)
-  // warps: epilogue 0-7 | A producers 8-15 | TMA 16 | MMA 17 | 18, 19 idle (they complete the warpgroup whose registers
-  // are handed to the epilogue warpgroups with setmaxnreg)
-  static constexpr int W_PROD0 = EPI_WARPS, W_TMA = EPI_WARPS + PROD_WARPS, W_MMA = W_TMA + 1;
-  static constexpr int THREADS = (W_TMA + 4) * 32;
-  static constexpr int EPI_REGS = 120, CTL_REGS = 40;  // per CTA pool: 128 x (96 - 40) released >= 256 x (120 - 96) requested
-  static_assert(PROD_WARPS == 8, "warp roles assume 8 producer warps (two per TMEM lane quarter)");
+  static constexpr int THREADS = (EPI_WARPS + 2 + PROD_WARPS) * 32;   // epilogue | TMA | MMA | A producers
+  static constexpr int W_TMA = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_PROD0 = EPI_WARPS + 2;
   static constexpr int NB = 2;                         // TMEM accumulator buffers (128 columns each): MMA runs one chunk ahead
   static constexpr uint32_t TM_ACC = 2 * A_COLS;       // columns: A buffer 0 | A buffer 1 | accumulator 0 | accumulator 1
   static constexpr uint32_t TMEM_COLS = TM_ACC + NB * BN;
@@ -151,7 +147,6 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
 
   if (warp < Cfg::EPI_WARPS) {
     // ============================ epilogue ============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::EPI_REGS));
     // One warp per scheduler could not hide its own ALU / TMEM / shared-memory latencies (the kernel ran at the
     // speed of this instruction stream even with loads, stores and MMAs removed), hence two warps per sub-partition:
     // warp w owns TMEM lanes 32 (w & 3) .. +31 (= tile rows) and the 64-column half (w >> 2) of every chunk.
@@ -178,10 +173,10 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         uint32_t r0[32], r1[32];
         tmem_ld32(tmem_base + lane_base + Cfg::TM_ACC + buf * Cfg::BN + chh * 64, r0);
         tmem_ld32(tmem_base + lane_base + Cfg::TM_ACC + buf * Cfg::BN + chh * 64 + 32, r1);
-        // Shared-memory loads are requested two steps ahead of their use (volatile asm keeps the order): under the
+        // Shared-memory loads are requested one step ahead of their use (volatile asm keeps the order): under the
         // MMA's operand traffic an LDS takes ~150 cycles, and a load-use pair per step left 8 + 3 of those
         // exposed per chunk (ncu source view: short-scoreboard stalls on the first FADD / STG after each LDS)
-        float4 b0 = lds_f4(bb), b1 = lds_f4(bb + 4), n0 = lds_f4(bb + 8), n1 = lds_f4(bb + 12);   // two steps in flight
+        float4 b0 = lds_f4(bb), b1 = lds_f4(bb + 4);
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(&acc_empty[buf]);               // accumulator columns are in registers: the MMA warp may refill the buffer
@@ -189,15 +184,15 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
 #pragma unroll
         for (int k8 = 0; k8 < 8; ++k8) {
           const uint32_t* r = (k8 < 4) ? (r0 + k8 * 8) : (r1 + (k8 - 4) * 8);
-          float4 m0 = n0, m1 = n1;
-          if (k8 < 6) { m0 = lds_f4(bb + (k8 + 2) * 8); m1 = lds_f4(bb + (k8 + 2) * 8 + 4); }
+          float4 n0 = b0, n1 = b1;
+          if (k8 < 7) { n0 = lds_f4(bb + (k8 + 1) * 8); n1 = lds_f4(bb + (k8 + 1) * 8 + 4); }
           uint4 pk;
           pk.x = pack_bf16x2(__uint_as_float(r[0]) + b0.x, __uint_as_float(r[1]) + b0.y);
           pk.y = pack_bf16x2(__uint_as_float(r[2]) + b0.z, __uint_as_float(r[3]) + b0.w);
           pk.z = pack_bf16x2(__uint_as_float(r[4]) + b1.x, __uint_as_float(r[5]) + b1.y);
           pk.w = pack_bf16x2(__uint_as_float(r[6]) + b1.z, __uint_as_float(r[7]) + b1.w);
           sts_u4(stg + lane * 128 + ((k8 ^ (lane & 7)) << 4), pk);
-          b0 = n0; b1 = n1; n0 = m0; n1 = m1;
+          b0 = n0; b1 = n1;
         }
         __syncwarp();
         if (threadIdx.x == 0) QKV_TS(0, ci * 5 + 3);
@@ -230,7 +225,81 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
         ++ci;
       }
     }
-  } else if (warp < Cfg::W_TMA) {
+  } else if (warp == Cfg::W_TMA) {
+    // ============================ TMA producer (weights) ============================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmap0); tma_prefetch_desc(&tmap1);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int a, tok0; uint32_t chunk_mask;
+        if (!tile_info(t, a, tok0, chunk_mask)) continue;
+        const CUtensorMap* tmap = (p.mode[a] != 0) ? &tmap1 : &tmap0;
+        for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
+          const int c = (cc + rot) % Cfg::N_CHUNKS;
+          if (!((chunk_mask >> c) & 1u)) continue;
+          for (int kc = 0; kc < Cfg::NCHA; kc += Cfg::SUB, ++it) {
+            const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
+            mbar_wait(&b_empty[s], ph ^ 1u);
+            if ((HMVIT_QKV_DBG & 2) && it >= Cfg::NS) { mbar_arrive(&b_full[s]); continue; }
+            mbar_arrive_expect_tx(&b_full[s], Cfg::STAGE);
+#pragma unroll
+            for (int j = 0; j < Cfg::SUB; ++j)
+              tma_load_2d(sB + s * Cfg::STAGE + j * Cfg::CHUNK, tmap, &b_full[s], (kc + j) * 64, c * Cfg::BN);
+          }
+        }
+      }
+    }
+  } else if (warp == Cfg::W_MMA) {
+    // ============================ MMA issuer ============================
+    // The whole warp runs the loop (uniform control flow); one elected lane issues the MMAs and commits.
+    {
+      constexpr uint32_t idesc = umma_idesc(1u, Cfg::BM, Cfg::BN);
+      const uint32_t b_base = smem_u32(sB);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+      uint32_t it = 0, ci = 0, ti = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int a, tok0; uint32_t chunk_mask;
+        if (!tile_info(t, a, tok0, chunk_mask)) continue;
+        const uint32_t ab = ti & 1u;
+        mbar_wait(&a_full[ab], (ti >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t a_tmem = tm + ab * Cfg::A_COLS;
+        for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
+          const int c = (cc + rot) % Cfg::N_CHUNKS;
+          if (!((chunk_mask >> c) & 1u)) continue;
+          const uint32_t buf = ci % Cfg::NB;
+          if (lane == 0) QKV_TS(1, ci * 3 + 0);
+          mbar_wait(&acc_empty[buf], ((ci / Cfg::NB) & 1u) ^ 1u);
+          tc_fence_after();
+          if (lane == 0) QKV_TS(1, ci * 3 + 1);
+          const uint32_t d_tmem = tm + Cfg::TM_ACC + buf * Cfg::BN;
+          for (int kc = 0; kc < Cfg::NCHA; kc += Cfg::SUB, ++it) {
+            const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
+            mbar_wait(&b_full[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+              if (!(HMVIT_QKV_DBG & 4)) {
+#pragma unroll
+                for (int j = 0; j < Cfg::SUB; ++j)
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks)
+                    umma_ts_bf16(d_tmem, a_tmem + (kc + j) * 32 + ks * 8,
+                                 umma_desc_sw128(b_base + s * Cfg::STAGE + j * Cfg::CHUNK + ks * 32), idesc, (kc | j | ks) != 0 ? 1u : 0u);
+              }
+              umma_commit(&b_empty[s]);
+              if (kc + Cfg::SUB >= Cfg::NCHA) umma_commit(&acc_full[buf]);
+            }
+            __syncwarp();
+          }
+          if (lane == 0) QKV_TS(1, ci * 3 + 2);
+          ++ci;
+        }
+        if (elect_one()) umma_commit(&a_empty[ab]);               // every MMA that reads this A buffer has retired
+        __syncwarp();
+        ++ti;
+      }
+    }
+  } else {
     // ============================ A producers: typed LayerNorm ============================
     // PROD_WARPS == 8: two threads per token row, each owns 128 channels -> twice the loads in flight per SM.
     // A warp can only touch the TMEM lane quarter (warp % 4), which fixes the rows it produces.
@@ -317,83 +386,6 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
       if (pidx == 0) QKV_TS(2, ti * 4 + 3);
       ++ti;
     }
-  } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::CTL_REGS));   // one instruction for the whole warpgroup (warps 16-19)
-  if (warp == Cfg::W_TMA) {
-    // ============================ TMA producer (weights) ============================
-    if (lane == 0) {
-      tma_prefetch_desc(&tmap0); tma_prefetch_desc(&tmap1);
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int a, tok0; uint32_t chunk_mask;
-        if (!tile_info(t, a, tok0, chunk_mask)) continue;
-        const CUtensorMap* tmap = (p.mode[a] != 0) ? &tmap1 : &tmap0;
-        for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
-          const int c = (cc + rot) % Cfg::N_CHUNKS;
-          if (!((chunk_mask >> c) & 1u)) continue;
-          for (int kc = 0; kc < Cfg::NCHA; kc += Cfg::SUB, ++it) {
-            const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
-            mbar_wait(&b_empty[s], ph ^ 1u);
-            if ((HMVIT_QKV_DBG & 2) && it >= Cfg::NS) { mbar_arrive(&b_full[s]); continue; }
-            mbar_arrive_expect_tx(&b_full[s], Cfg::STAGE);
-#pragma unroll
-            for (int j = 0; j < Cfg::SUB; ++j)
-              tma_load_2d(sB + s * Cfg::STAGE + j * Cfg::CHUNK, tmap, &b_full[s], (kc + j) * 64, c * Cfg::BN);
-          }
-        }
-      }
-    }
-  } else if (warp == Cfg::W_MMA) {
-    // ============================ MMA issuer ============================
-    // The whole warp runs the loop (uniform control flow); one elected lane issues the MMAs and commits.
-    {
-      constexpr uint32_t idesc = umma_idesc(1u, Cfg::BM, Cfg::BN);
-      const uint32_t b_base = smem_u32(sB);
-      const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-      uint32_t it = 0, ci = 0, ti = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int a, tok0; uint32_t chunk_mask;
-        if (!tile_info(t, a, tok0, chunk_mask)) continue;
-        const uint32_t ab = ti & 1u;
-        mbar_wait(&a_full[ab], (ti >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t a_tmem = tm + ab * Cfg::A_COLS;
-        for (int cc = 0; cc < Cfg::N_CHUNKS; ++cc) {
-          const int c = (cc + rot) % Cfg::N_CHUNKS;
-          if (!((chunk_mask >> c) & 1u)) continue;
-          const uint32_t buf = ci % Cfg::NB;
-          if (lane == 0) QKV_TS(1, ci * 3 + 0);
-          mbar_wait(&acc_empty[buf], ((ci / Cfg::NB) & 1u) ^ 1u);
-          tc_fence_after();
-          if (lane == 0) QKV_TS(1, ci * 3 + 1);
-          const uint32_t d_tmem = tm + Cfg::TM_ACC + buf * Cfg::BN;
-          for (int kc = 0; kc < Cfg::NCHA; kc += Cfg::SUB, ++it) {
-            const uint32_t s = it % Cfg::NS, ph = (it / Cfg::NS) & 1u;
-            mbar_wait(&b_full[s], ph);
-            tc_fence_after();
-            if (elect_one()) {
-              if (!(HMVIT_QKV_DBG & 4)) {
-#pragma unroll
-                for (int j = 0; j < Cfg::SUB; ++j)
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks)
-                    umma_ts_bf16(d_tmem, a_tmem + (kc + j) * 32 + ks * 8,
-                                 umma_desc_sw128(b_base + s * Cfg::STAGE + j * Cfg::CHUNK + ks * 32), idesc, (kc | j | ks) != 0 ? 1u : 0u);
-              }
-              umma_commit(&b_empty[s]);
-              if (kc + Cfg::SUB >= Cfg::NCHA) umma_commit(&acc_full[buf]);
-            }
-            __syncwarp();
-          }
-          if (lane == 0) QKV_TS(1, ci * 3 + 2);
-          ++ci;
-        }
-        if (elect_one()) umma_commit(&a_empty[ab]);               // every MMA that reads this A buffer has retired
-        __syncwarp();
-        ++ti;
-      }
-    }
-  }
   }
 
   tc_fence_before();
