@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
       //      projection MMAs have finished (and were L2-prefetched during the previous tile) ----
       float rv[64];
 #pragma unroll
-      for (int k = 0; k < 64; ++k) rv[k] = (valid && !(HMVIT_CHAIN_DBG & 8)) ? res[static_cast<size_t>(k) * p.N] : 0.f;
+      for (int k = 0; k < 64; ++k) rv[k] = (valid && !(HMVIT_CHAIN_DBG & 8)) ? res[k * p.N] : 0.f;
       float rstd = 1.f, nmr = 0.f;
       if constexpr (!kHead) {
         if (threadIdx.x == 0) CHAIN_TS(0, ti, 0);
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
           if (k == 0) t0 = v;
           const float d = v - t0;
           tsum += d; tsq += d * d;
-          if (valid && (!(HMVIT_CHAIN_DBG & 1) || v == 12345.678f)) dst[static_cast<size_t>(k) * p.N] = v;
+          if (valid && (!(HMVIT_CHAIN_DBG & 1) || v == 12345.678f)) dst[k * p.N] = v;
         }
       }
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 7);
