@@ -8,9 +8,11 @@
 //                         shared-memory image the attention kernel wants (one 16 KB blob per tile x head group).
 //                         Small CTAs, few registers -> many warps per SM, which is what the tap gather needs
 //                         (profiles/r1_attention_study.md: gather bandwidth scales with gathering warps per SM).
-//   dense_attn_kernel     one CTA per (b, i, g, head group of 4 heads).  Per 64-key tile: two 16 KB bulk copies
-//                         (cp.async.bulk -> mbarrier), S = Q K^T + relative position bias (looked up through
-//                         the tile's key-slot list), online softmax, O += P V with mma.sync bf16 tiles.
+//   dense_attn_kernel     one CTA per (b, i, g, head group of 4 heads), warp == head.  Per 64-key tile: two 16 KB
+//                         bulk copies (cp.async.bulk -> mbarrier, K and V double buffered), the tile's K / V
+//                         fragments read from shared memory ONCE and held in registers for the four 16-row query
+//                         blocks, S = Q K^T + relative position bias (looked up through the tile's key-slot list,
+//                         prefetched one tile ahead), online softmax, O += P V with mma.sync bf16 tiles.
 //                         No key mask inside a tile: only the tail of the last tile is masked.
 //
 // Replaces hetero_fusion.py:338-361 (warp_features) + :187-277 (HeteroAttention.forward core).  Compared with
