@@ -74,6 +74,14 @@ def test_packed_weights_match_emulation_folding():
     assert int((w1.view(torch.int32) & 0x1FFF).abs().max()) == 0
     g2 = P["hetero_fusion_block.grid_ffd.norm.net.0.weight"]
     assert float((w1 - P["hetero_fusion_block.grid_ffd.fn.net.0.0.weight"] * g2[None, :]).abs().max()) < 1e-3
+    # fp16 copies for the fused chain kernel: same 11-bit significand as tf32 -> they agree with the tf32 copies to one
+    # ulp of that format wherever fp16 is normal (|w| >= 2^-14), and no weight overflows
+    for key in ("w1", "w2"):
+        for t in (0, 1):
+            h, f = pk[f"{key}h_{t}"], pk[f"{key}_{t}"]
+            assert h.dtype == torch.float16 and h.shape == f.shape and bool(torch.isfinite(h).all())
+            normal = f.abs() >= 2.0 ** -14
+            assert float(((h.float() - f).abs() / f.abs().clamp_min(1e-30))[normal].max()) <= 2.0 ** -10
 
 
 def test_regroup_matches_oracle():
