@@ -17,7 +17,7 @@
 // the head group and the key half (w >> 2) of every source.  Round-1 kernel: correctness first.
 #pragma once
 #include "attn.cuh"
-#include <mma.h>
+#include "wmma_shared.cuh"
 
 #ifndef HMVIT_BWD_DBG   // bottleneck-hunting builds only (results are wrong): 1 no shared bias-gradient atomics, 2 no global scatter
 #define HMVIT_BWD_DBG 0
@@ -223,10 +223,10 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
           for (int ks = 0; ks < 2; ++ks) {
             wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fq, fg;
             wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> fk, fv;
-            wmma::load_matrix_sync(fq, sQ + (mt * 16) * Cfg::LD + hl * 32 + ks * 16, Cfg::LD);
-            wmma::load_matrix_sync(fg, sdO + (mt * 16) * Cfg::LD + hl * 32 + ks * 16, Cfg::LD);
-            wmma::load_matrix_sync(fk, sK + (kc * 16) * Cfg::LD + hl * 32 + ks * 16, Cfg::LD);
-            wmma::load_matrix_sync(fv, sV + (kc * 16) * Cfg::LD + hl * 32 + ks * 16, Cfg::LD);
+            wmma_load_shared(fq, sQ + (mt * 16) * Cfg::LD + hl * 32 + ks * 16, Cfg::LD);
+            wmma_load_shared(fg, sdO + (mt * 16) * Cfg::LD + hl * 32 + ks * 16, Cfg::LD);
+            wmma_load_shared(fk, sK + (kc * 16) * Cfg::LD + hl * 32 + ks * 16, Cfg::LD);
+            wmma_load_shared(fv, sV + (kc * 16) * Cfg::LD + hl * 32 + ks * 16, Cfg::LD);
             wmma::mma_sync(sacc, fq, fk, sacc);
             wmma::mma_sync(pacc, fg, fv, pacc);
           }
@@ -264,11 +264,11 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
           wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> fs;
-          wmma::load_matrix_sync(fs, sdSb + mt * 256, 16);
+          wmma_load_shared(fs, sdSb + mt * 256, 16);
 #pragma unroll
           for (int nt = 0; nt < 2; ++nt) {
             wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fk;
-            wmma::load_matrix_sync(fk, sK + (kc * 16) * Cfg::LD + hl * 32 + nt * 16, Cfg::LD);
+            wmma_load_shared(fk, sK + (kc * 16) * Cfg::LD + hl * 32 + nt * 16, Cfg::LD);
             wmma::mma_sync(dq[mt][nt], fs, fk, dq[mt][nt]);
           }
         }
@@ -280,13 +280,13 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> fst, fpt;
-            wmma::load_matrix_sync(fst, sdSb + ks * 256, 16);
-            wmma::load_matrix_sync(fpt, sPb + ks * 256, 16);
+            wmma_load_shared(fst, sdSb + ks * 256, 16);
+            wmma_load_shared(fpt, sPb + ks * 256, 16);
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
               wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> fq, fg;
-              wmma::load_matrix_sync(fq, sQ + (ks * 16) * Cfg::LD + hl * 32 + nt * 16, Cfg::LD);
-              wmma::load_matrix_sync(fg, sdO + (ks * 16) * Cfg::LD + hl * 32 + nt * 16, Cfg::LD);
+              wmma_load_shared(fq, sQ + (ks * 16) * Cfg::LD + hl * 32 + nt * 16, Cfg::LD);
+              wmma_load_shared(fg, sdO + (ks * 16) * Cfg::LD + hl * 32 + nt * 16, Cfg::LD);
               wmma::mma_sync(kacc[nt], fst, fq, kacc[nt]);
               wmma::mma_sync(vacc[nt], fpt, fg, vacc[nt]);
             }

@@ -13,7 +13,7 @@
 // bf16 [agents*N][256].  All kernels are typed by mode[a] and skip padded agent slots.
 #pragma once
 #include "common.cuh"
-#include <mma.h>
+#include "wmma_shared.cuh"
 
 namespace hmvit {
 
@@ -264,14 +264,14 @@ __global__ void __launch_bounds__(256, HMVIT_WG_MINB) wgrad_kernel(const WgradPa
       wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, typename std::conditional<B_ROWS, wmma::row_major, wmma::col_major>::type> fb[2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        if constexpr (B_ROWS) wmma::load_matrix_sync(fb[j], tB + kk * kWgLdM + wn + j * 16, kWgLdM);
-        else wmma::load_matrix_sync(fb[j], tB + (wn + j * 16) * kWgLdK + kk, kWgLdK);
+        if constexpr (B_ROWS) wmma_load_shared(fb[j], tB + kk * kWgLdM + wn + j * 16, kWgLdM);
+        else wmma_load_shared(fb[j], tB + (wn + j * 16) * kWgLdK + kk, kWgLdK);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {          // one A fragment live at a time (register budget: 2 CTAs / SM)
         wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, typename std::conditional<A_ROWS, wmma::col_major, wmma::row_major>::type> fa;
-        if constexpr (A_ROWS) wmma::load_matrix_sync(fa, tA + kk * kWgLdM + wm + i * 16, kWgLdM);
-        else wmma::load_matrix_sync(fa, tA + (wm + i * 16) * kWgLdK + kk, kWgLdK);
+        if constexpr (A_ROWS) wmma_load_shared(fa, tA + kk * kWgLdM + wm + i * 16, kWgLdM);
+        else wmma_load_shared(fa, tA + (wm + i * 16) * kWgLdK + kk, kWgLdK);
 #pragma unroll
         for (int j = 0; j < 2; ++j) wmma::mma_sync(acc[i][j], fa, fb[j], acc[i][j]);
       }
