@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
           float pr = 0.f, dsn = 0.f;
           if ((rec.w01 | rec.w23) != 0u) {
             const int rel = ((s >> 3) - (sp >> 3) + 7) * 15 + ((s & 7) - (sp & 7) + 7);
-            pr = exp2f(sS[idx] + sBias[hl * kBiasStride + rel] - sLse[hl * kS + s]);
+            pr = ex2(sS[idx] + sBias[hl * kBiasStride + rel] - sLse[hl * kS + s]);
             dsn = pr * (sdP[idx] - sD[hl * kS + s]);
 #if !(HMVIT_BWD_DBG & 1)
             sBgW[rel] += dsn;
