@@ -187,17 +187,26 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
             const uint32_t wq[4] = {rec.w01 & 0xffffu, rec.w01 >> 16, rec.w23 & 0xffffu, rec.w23 >> 16};
             ko = make_uint4(bk2[0], bk2[1], bk2[2], bk2[3]);
             vo = make_uint4(bv2[0], bv2[1], bv2[2], bv2[3]);
+            // all eight tap loads of the token are in flight before the first blend (a load-use pair per tap exposed
+            // four global latencies per token; same taps, order and arithmetic as the forward)
+            uint4 kk[4], vv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              kk[q] = make_uint4(0, 0, 0, 0); vv[q] = make_uint4(0, 0, 0, 0);
+              if (wq[q] != 0u) {
+                const int yy = rec.y0 + (q >> 1), xx = rec.x0 + (q & 1);
+                const size_t off = static_cast<size_t>(yy * p.W + xx) * 32;
+                kk[q] = __ldg(ksrc + off); vv[q] = __ldg(vsrc + off);
+              }
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (wq[q] == 0u) continue;
-              const int yy = rec.y0 + (q >> 1), xx = rec.x0 + (q & 1);
-              const size_t off = static_cast<size_t>(yy * p.W + xx) * 32;
-              const uint4 kk = __ldg(ksrc + off), vv = __ldg(vsrc + off);
               const uint32_t w2 = wq[q] | (wq[q] << 16);
-              ko.x = hfma2_bf16(w2, kk.x, ko.x); ko.y = hfma2_bf16(w2, kk.y, ko.y);
-              ko.z = hfma2_bf16(w2, kk.z, ko.z); ko.w = hfma2_bf16(w2, kk.w, ko.w);
-              vo.x = hfma2_bf16(w2, vv.x, vo.x); vo.y = hfma2_bf16(w2, vv.y, vo.y);
-              vo.z = hfma2_bf16(w2, vv.z, vo.z); vo.w = hfma2_bf16(w2, vv.w, vo.w);
+              ko.x = hfma2_bf16(w2, kk[q].x, ko.x); ko.y = hfma2_bf16(w2, kk[q].y, ko.y);
+              ko.z = hfma2_bf16(w2, kk[q].z, ko.z); ko.w = hfma2_bf16(w2, kk[q].w, ko.w);
+              vo.x = hfma2_bf16(w2, vv[q].x, vo.x); vo.y = hfma2_bf16(w2, vv[q].y, vo.y);
+              vo.z = hfma2_bf16(w2, vv[q].z, vo.z); vo.w = hfma2_bf16(w2, vv[q].w, vo.w);
             }
           }
           *reinterpret_cast<uint4*>(sK + s * Cfg::LD + u16 * 8) = ko;
