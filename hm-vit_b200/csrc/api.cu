@@ -186,7 +186,9 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
 // ------------------------------------------------------------------------------------------------
 // fused output projection + FFN chain
 // ------------------------------------------------------------------------------------------------
-extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
+// `h` != NULL (internal, hmvit_fusion_forward only): the ego tiles of the last stage also run the feed-forward head in
+// the same launch (chain_kernel<2>); the block output `a->out` is then not written.
+static int launch_chain(const HmvitChainArgs* a, const HmvitHeadArgs* h, void* stream) {
   HMVIT_CHECK_ARG(a != nullptr, "chain: null args");
   HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->N > 0, "chain: B, L, N must be positive");
   HMVIT_CHECK_ARG(a->mode && a->record_len && a->o && a->resid && a->out && a->wa[0] && a->wa[1] && a->ba && a->w1[0] && a->w1[1] && a->b1 && a->w2[0] && a->w2[1] && a->b2, "chain: null pointer");
@@ -196,24 +198,37 @@ extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) {
     rc = make_weight_tmap(&maps.wa[t], a->wa[t], 256, 2, 256); if (rc) return rc;
     rc = make_weight_tmap(&maps.w1[t], a->w1[t], 256, 2, 256, true); if (rc) return rc;
     rc = make_weight_tmap(&maps.w2[t], a->w2[t], 256, 2, 256, true); if (rc) return rc;
+    if (h != nullptr) {
+      rc = make_weight_tmap(&maps.hw1[t], h->w1[t], 256, 2, 256, true); if (rc) return rc;
+      rc = make_weight_tmap(&maps.hw2[t], h->w2[t], 256, 2, 256, true); if (rc) return rc;
+    } else {
+      maps.hw1[t] = maps.w1[t]; maps.hw2[t] = maps.w2[t];        // unused by the other instances
+    }
   }
   ChainParams p;
   p.B = a->B; p.L = a->L; p.N = a->N; p.mode = a->mode; p.record_len = a->record_len; p.tile_ego_only = a->ego_only ? 1 : 0;
   p.resid_cm = a->resid; p.out_cm = a->out; p.ba = a->ba; p.ln_gamma = a->ln_gamma; p.ln_beta = a->ln_beta; p.ln_eps = a->ln_eps;
   p.b1 = a->b1; p.b2 = a->b2; p.stats_out = reinterpret_cast<float2*>(a->stats_out); p.out_L = a->L;
+  p.hb1 = h ? h->b1 : nullptr; p.hb2 = h ? h->b2 : nullptr; p.head_out = h ? h->out : nullptr;
+  if (h != nullptr) HMVIT_CHECK_ARG(a->ego_only && h->b1 && h->b2 && h->out, "chain: the fused head needs the ego-only stage and its biases / output");
   HMVIT_CHECK_ARG((a->ln_gamma == nullptr) == (a->ln_beta == nullptr), "chain: ln_gamma and ln_beta must both be set or both be null");
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES);
   });
   HMVIT_CHECK_CUDA(attr_err);
   const long long tiles = static_cast<long long>(a->B) * a->L * ((a->N + ChainCfg::BM - 1) / ChainCfg::BM);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  chain_kernel<false><<<grid, ChainCfg::THREADS, ChainCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(maps, p);
+  if (h != nullptr) chain_kernel<2><<<grid, ChainCfg::THREADS, ChainCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(maps, p);
+  else chain_kernel<0><<<grid, ChainCfg::THREADS, ChainCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(maps, p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }
+
+extern "C" int hmvit_out_ffn_chain(const HmvitChainArgs* a, void* stream) { return launch_chain(a, nullptr, stream); }
 
 // ------------------------------------------------------------------------------------------------
 // typed feed-forward head on the ego rows (the chain kernel without projection, LayerNorm and residual)
@@ -238,12 +253,12 @@ extern "C" int hmvit_ffn_head(const HmvitHeadArgs* a, void* stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES);
   });
   HMVIT_CHECK_CUDA(attr_err);
   const long long tiles = static_cast<long long>(a->B) * a->L * ((a->N + ChainCfg::BM - 1) / ChainCfg::BM);
   const int grid = static_cast<int>(tiles < num_sms() ? tiles : num_sms());
-  chain_kernel<true><<<grid, ChainCfg::THREADS, ChainCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(maps, p);
+  chain_kernel<1><<<grid, ChainCfg::THREADS, ChainCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(maps, p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }
@@ -425,8 +440,20 @@ static bool split_attention() {
   return on;
 }
 
+// HMVIT_FUSE_HEAD=0 keeps the head as its own launch (A/B measurements).
+static bool fuse_head_enabled() {
+  static bool on = [] { const char* e = getenv("HMVIT_FUSE_HEAD"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
+static bool fuse_head(const HmvitFusionArgs* a) {
+  return fuse_head_enabled() && a->head && !a->unfused && a->skip_dead && a->head_w1h[0] && a->head_w1h[1] && a->head_w2h[0] &&
+         a->head_w2h[1] && a->head_b1 && a->head_b2 && a->out;
+}
+
+/* head: 0 = no head, 1 = head as its own launch, 2 = head with skip_dead (fused into the last stage's chain launch) */
 extern "C" int hmvit_fusion_launch_count(int32_t num_iters, int32_t head) {
-  return num_iters * 2 * (split_attention() ? 4 : 3) + (head ? 1 : 0);
+  const int head_launch = head == 0 ? 0 : ((head == 2 && fuse_head_enabled()) ? 0 : 1);
+  return num_iters * 2 * (split_attention() ? 4 : 3) + head_launch;
 }
 
 static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream);
@@ -486,6 +513,7 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
   ws += align_up(rows * 2 * 4, 1024);
   void* attn_ws = (a->L <= kSplitMaxL && split_attention()) ? ws : nullptr;
   bool have_stats = false;                        // stats describe the rows currently in xres
+  bool head_done = false;                         // the head ran inside the last stage's chain launch
 
   for (int it = 0; it < a->num_iters; ++it) {
     for (int kind = 0; kind < 2; ++kind) {
@@ -530,12 +558,24 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
         HMVIT_CHECK_ARG(w.w1h[0] && w.w1h[1] && w.w2h[0] && w.w2h[1], "fusion_forward: fp16 feed-forward weights (w1h / w2h) missing");
         c.w1[0] = w.w1h[0]; c.w1[1] = w.w1h[1]; c.b1 = w.b1; c.w2[0] = w.w2h[0]; c.w2[1] = w.w2h[1]; c.b2 = w.b2;
         c.stats_out = stats;
-        rc = hmvit_out_ffn_chain(&c, stream); if (rc) return rc;
+        const bool last = (it == a->num_iters - 1 && kind == 1);
+        if (last && dead && fuse_head(a)) {
+          // last stage on the ego tiles only: the head runs inside the same launch
+          HmvitHeadArgs h;
+          memset(&h, 0, sizeof(h));
+          h.B = a->B; h.L = a->L; h.N = N; h.mode = a->mode; h.record_len = a->record_len; h.x = a->xres;
+          h.w1[0] = a->head_w1h[0]; h.w1[1] = a->head_w1h[1]; h.b1 = a->head_b1;
+          h.w2[0] = a->head_w2h[0]; h.w2[1] = a->head_w2h[1]; h.b2 = a->head_b2; h.out = a->out;
+          rc = launch_chain(&c, &h, stream); if (rc) return rc;
+          head_done = true;
+        } else {
+          rc = launch_chain(&c, nullptr, stream); if (rc) return rc;
+        }
         have_stats = true;
       }
     }
   }
-  if (a->head) {
+  if (a->head && !head_done) {
     HMVIT_CHECK_ARG(a->head_w1[0] && a->head_w1[1] && a->head_w2[0] && a->head_w2[1] && a->head_b1 && a->head_b2,
                     "fusion_forward: head weights missing");
     if (a->unfused) {

@@ -59,6 +59,9 @@ struct ChainParams {
   const float* b2;             // [2][256]
   float2* stats_out;           // optional [B*L][N] (mean, rstd) of every x'' row: LayerNorm statistics for the next stage
   int out_L;                   // agent slots per scene in out_cm (L; 1 for the head, whose output is [B][256][N])
+  const float* hb1;            // fused head (mode 2): [2][256] biases and the [B][256][N] output
+  const float* hb2;
+  float* head_out;
 };
 
 struct ChainMaps {             // TMA tensor maps
@@ -66,6 +69,8 @@ struct ChainMaps {             // TMA tensor maps
   CUtensorMap wa[2];           // bf16 [256][256], box 64 x 256
   CUtensorMap w1[2];           // fp16 [256][256], box 64 x 256
   CUtensorMap w2[2];
+  CUtensorMap hw1[2];          // fused head (mode 2): fp16 [256][256] head weights
+  CUtensorMap hw2[2];
 };
 
 struct ChainCfg {
@@ -78,7 +83,7 @@ struct ChainCfg {
   static constexpr int NS = 2;                        // weight ring stages (32 KB each)
   static constexpr int AO_BYTES = 4 * CHUNK;          // O tile, bf16
   static constexpr int PART_BYTES = 4 * 128 * 8;      // per-group partial LN statistics
-  static constexpr int BIAS_BYTES = 3 * 2 * 256 * 4;   // ba | b1 | b2, both types: read by every transform thread
+  static constexpr int BIAS_BYTES = 5 * 2 * 256 * 4;   // ba | b1 | b2 | head b1 | head b2, both types: read by every transform thread
   static constexpr int SMEM_BYTES = AO_BYTES + NF * CHUNK + NS * WSTAGE + PART_BYTES + BIAS_BYTES + 256 + 1024;
   static constexpr int NT = 512;                      // transform threads
   static constexpr int THREADS = NT + 128;            // 16 transform warps + one warpgroup holding the TMA and MMA warps (2 idle)
@@ -96,9 +101,13 @@ HMVIT_DEVINL float2 ln_combine(const float2* part, int row, float eps) {
 // kHead: the typed feed-forward HEAD of the fusion module (HeteroFusion.mlp_head, bevformer_point_pillar_hetero.py:36,
 // 47-48): y = W_2 gelu(W_1 x + b_1) + b_2 on the ego rows -- the same pipeline without the output projection (P1),
 // without LayerNorm and without the residual (P3 overwrites D1 instead of accumulating onto x').
-template <bool kHead>
+// kMode 2: the normal chain on the ego tiles of the LAST stage followed, in the same tile, by the head: x'' is not
+// stored but fed (fp16) into two more GEMM phases, P4: D2 = x'' Wh_1^T, P5: D1 = gelu(D2 + bh_1) Wh_2^T, and
+// E3 writes D1 + bh_2 to the [B][256][N] output.  Saves the head's launch and its pipeline fill / drain (3.6 tiles per SM).
+template <int kMode>
 __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __grid_constant__ ChainMaps maps, const ChainParams p) {
   using Cfg = ChainCfg;
+  constexpr bool kHead = kMode == 1, kFuse = kMode == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_align1024(smem_raw);
   uint8_t* sO = smem;
@@ -131,6 +140,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
   // biases in shared memory (a global load per use showed up as long-scoreboard stalls of the transform warps)
   for (int e = threadIdx.x; e < 2 * kC; e += Cfg::THREADS) {
     sBias[e] = __ldg(p.ba + e); sBias[2 * kC + e] = __ldg(p.b1 + e); sBias[4 * kC + e] = __ldg(p.b2 + e);
+    if constexpr (kFuse) { sBias[6 * kC + e] = __ldg(p.hb1 + e); sBias[8 * kC + e] = __ldg(p.hb2 + e); }
   }
   tc_fence_before();
   __syncthreads();
@@ -254,7 +264,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
       prefetch_resid_l2(t_next);
       // ---- P3 feed: gelu(D2 + b_1) -> fp16 K-chunk gq ----
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 3);
-      mbar_wait(d2_full, ti & 1);
+      mbar_wait(d2_full, kFuse ? 0u : (ti & 1));     // mode 2: two completions per tile (P2, P4)
       tc_fence_after();
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 4);
       const float* b1 = sBias + 2 * kC + type * kC + c0;
@@ -282,11 +292,75 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
       }
       // ---- E2: x'' = D1 + b_2 on this group's 64 columns (+ LayerNorm statistics of x'') ----
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 5);
-      mbar_wait(d1_final, ti & 1);
+      mbar_wait(d1_final, kFuse ? 0u : (ti & 1));    // mode 2: two completions per tile (P3, P5)
       tc_fence_after();
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 6);
       const float* b2 = sBias + 4 * kC + type * kC + c0;
       float t0 = 0.f, tsum = 0.f, tsq = 0.f;
+      if constexpr (kFuse) {
+        // ---- P4 feed: x'' = D1 + b_2 -> fp16 K-chunk gq (x'' is not stored: the head is its only consumer) ----
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld32(D1 + lane_base + c0, r0);
+          tmem_ld32(D1 + lane_base + c0 + 32, r1);
+          tmem_ld_wait();
+          uint32_t h2[32];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            h2[k] = pack_f16x2(__uint_as_float(r0[2 * k]) + b2[2 * k], __uint_as_float(r0[2 * k + 1]) + b2[2 * k + 1]);
+            h2[16 + k] = pack_f16x2(__uint_as_float(r1[2 * k]) + b2[32 + 2 * k], __uint_as_float(r1[2 * k + 1]) + b2[32 + 2 * k + 1]);
+          }
+          mbar_wait(&f_empty[gq], 1u);               // generation 4 ti + 2
+          uint8_t* dstF = sF + gq * Cfg::CHUNK;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<uint4*>(dstF + sw128_offset(row, u)) = make_uint4(h2[u * 4], h2[u * 4 + 1], h2[u * 4 + 2], h2[u * 4 + 3]);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(&f_full[gq]);
+        }
+        // ---- P5 feed: gelu(D2 + bh_1) -> fp16 K-chunk gq ----
+        mbar_wait(d2_full, 1u);
+        tc_fence_after();
+        {
+          const float* hb1 = sBias + 6 * kC + type * kC + c0;
+          uint32_t h2[32];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[32];
+            tmem_ld32(D2 + lane_base + c0 + hf * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              h2[hf * 16 + k] = pack_f16x2(gelu_erf_fast(__uint_as_float(r[2 * k]) + hb1[hf * 32 + 2 * k]),
+                                           gelu_erf_fast(__uint_as_float(r[2 * k + 1]) + hb1[hf * 32 + 2 * k + 1]));
+          }
+          mbar_wait(&f_empty[gq], 0u);               // generation 4 ti + 3
+          uint8_t* dstF = sF + gq * Cfg::CHUNK;
+#pragma unroll
+          for (int u = 0; u < 8; ++u)
+            *reinterpret_cast<uint4*>(dstF + sw128_offset(row, u)) = make_uint4(h2[u * 4], h2[u * 4 + 1], h2[u * 4 + 2], h2[u * 4 + 3]);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(&f_full[gq]);
+        }
+        // ---- E3: head output = D1 + bh_2 on this group's 64 columns ----
+        mbar_wait(d1_final, 1u);
+        tc_fence_after();
+        {
+          const float* hb2 = sBias + 8 * kC + type * kC + c0;
+          float* hdst = p.head_out + static_cast<size_t>(a / p.L) * kC * p.N + static_cast<size_t>(c0) * p.N + (valid ? tok : 0);
+          uint32_t r0[32], r1[32];
+          tmem_ld32(D1 + lane_base + c0, r0);
+          tmem_ld32(D1 + lane_base + c0 + 32, r1);
+          tmem_ld_wait();
+          tc_fence_before();
+          mbar_arrive(d1_free);                      // D1 is in registers: the next tile's projection may start
+#pragma unroll
+          for (int k = 0; k < 64; ++k)
+            if (valid) hdst[k * p.N] = __uint_as_float(k < 32 ? r0[k] : r1[k - 32]) + hb2[k];
+        }
+      } else
       {
         uint32_t r0[32], r1[32];
         tmem_ld32(D1 + lane_base + c0, r0);
@@ -304,7 +378,7 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         }
       }
       if (threadIdx.x == 0) CHAIN_TS(0, ti, 7);
-      if (p.stats_out != nullptr) {
+      if (!kFuse && p.stats_out != nullptr) {
         const float tmd = tsum * (1.0f / 64.0f);
         sPart[gq * 128 + row] = make_float2(t0 + tmd, fmaxf(tsq - tsum * tmd, 0.f));
         named_bar_sync(1, Cfg::NT);
@@ -343,6 +417,10 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         if constexpr (!kHead) for (int kc = 0; kc < 4; ++kc) wstage(&maps.wa[type], kc * 64);
         for (int j = 0; j < 4; ++j) wstage(&maps.w1[type], j * 64);   // K-chunk j == transform group j, same order as the MMA issuer
         for (int j = 0; j < 4; ++j) wstage(&maps.w2[type], j * 64);
+        if constexpr (kFuse) {
+          for (int j = 0; j < 4; ++j) wstage(&maps.hw1[type], j * 64);
+          for (int j = 0; j < 4; ++j) wstage(&maps.hw2[type], j * 64);
+        }
         ++ti;
       }
     }
@@ -380,10 +458,10 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
         }
         CHAIN_TS(1, ti, 3);
         // P2: D2 = LN'(x') W_1^T      P3: D1 += gelu(.) W_2^T     (4 stages of 64 K-columns each)
-        for (int phase = 0; phase < 2; ++phase) {
-          const uint32_t dacc = phase == 0 ? D2 : D1;
+        for (int phase = 0; phase < (kFuse ? 4 : 2); ++phase) {   // mode 2: + P4 (D2 = x'' Wh_1^T) and P5 (D1 = gelu(.) Wh_2^T)
+          const uint32_t dacc = (phase & 1) == 0 ? D2 : D1;
           for (int j = 0; j < 4; ++j, ++itw) {
-            const uint32_t fs = j, fph = phase;                  // generation 2 ti + phase of ring stage j
+            const uint32_t fs = j, fph = phase & 1;              // generation (2 | 4) ti + phase of ring stage j
             const uint32_t s = itw % Cfg::NS, ph = (itw / Cfg::NS) & 1u;
             mbar_wait(&f_full[fs], fph);
             mbar_wait(&w_full[s], ph);
@@ -393,12 +471,12 @@ __global__ void __launch_bounds__(ChainCfg::THREADS, 1) chain_kernel(const __gri
             for (int ks = 0; ks < 4; ++ks)
               umma_ss<2>(dacc, umma_desc_sw128(f_base + fs * Cfg::CHUNK + ks * 32),
                          umma_desc_sw128(w_base + s * Cfg::WSTAGE + ks * 32), idesc_f16,
-                         ((phase == 1 && !kHead) || (j | ks) != 0) ? 1u : 0u);
+                         ((phase == 1 && !kHead) || (j | ks) != 0) ? 1u : 0u);   // P3 accumulates onto x'; P4 / P5 overwrite
             umma_commit(&w_empty[s]);
             umma_commit(&f_empty[fs]);
           }
-          umma_commit(phase == 0 ? d2_full : d1_final);
-          CHAIN_TS(1, ti, 4 + phase);
+          umma_commit((phase & 1) == 0 ? d2_full : d1_final);
+          if (phase < 2) CHAIN_TS(1, ti, 4 + phase);
         }
         ++ti;
       }

@@ -216,8 +216,10 @@ def fusion_workspace_bytes(B, L, H, W) -> int:
     return int(_lib.load().hmvit_fusion_workspace_bytes(B, L, H, W))
 
 
-def fusion_launch_count(num_iters, head) -> int:
-    return int(_lib.load().hmvit_fusion_launch_count(num_iters, 1 if head else 0))
+def fusion_launch_count(num_iters, head, skip_dead=True) -> int:
+    """Kernel launches of one hmvit_fusion_forward.  With skip_dead (the module default) the head runs inside the last
+    stage's chain launch instead of a launch of its own."""
+    return int(_lib.load().hmvit_fusion_launch_count(num_iters, (2 if skip_dead else 1) if head else 0))
 
 
 def debug_probe(device="cuda"):

@@ -224,7 +224,8 @@ typedef struct {
 
 size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W);
 int hmvit_fusion_forward(const HmvitFusionArgs* args, void* stream);
-/* number of kernel launches one hmvit_fusion_forward enqueues (for launch accounting) */
+/* number of kernel launches one hmvit_fusion_forward enqueues (for launch accounting); head: 0 = no head, 1 = head as
+ * its own launch (skip_dead == 0 or unfused), 2 = head with skip_dead (runs inside the last stage's chain launch) */
 int hmvit_fusion_launch_count(int32_t num_iters, int32_t head);
 
 /* ---- backward pass (training configuration) ---------------------------------------------------------
