@@ -101,3 +101,15 @@ def test_emulation_restructuring_is_exact():
     yo = O.hetero_fusion(x, T, mode, rl, mask, P, cfg)
     ye = E.hetero_fusion(x, T, mode, rl, mask, P, cfg)
     assert float((ye - yo).norm() / yo.norm()) < 5e-6
+
+
+def test_launch_accounting():
+    """hmvit_fusion_launch_count is pure host code: per stage QKV + compaction + dense attention + chain; the head is a
+    launch of its own only without dead-query elimination (with it, it runs inside the last stage's chain launch)."""
+    pkg = hmvit_loader.load()
+    ops = pkg.ops
+    assert ops.fusion_launch_count(2, False) == 16
+    assert ops.fusion_launch_count(2, True, skip_dead=False) == 17
+    assert ops.fusion_launch_count(2, True, skip_dead=True) == 16
+    assert ops.fusion_launch_count(1, True) == 8
+
