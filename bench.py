@@ -136,6 +136,31 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ragged_variant(net, dev, batch, steps, warmup):
+    """the same forward with record_len ~ U{2..5} per scene (padded slots and their ego
+    passes are skipped exactly); device-resident, CUDA events.  A reported side figure, never the headline:
+    a failure here is recorded in the line instead of aborting the bench."""
+    try:
+        g = torch.Generator().manual_seed(4321)
+        rl = torch.randint(2, L + 1, (batch,), generator=g).tolist()
+        x, T, mode, rlt, mask = make_inputs(1234 + 2 + 500, batch, rl)
+        inp = [t.to(dev) for t in (x, T, mode, rlt.to(torch.int32), mask.to(torch.int32))]
+        for _ in range(max(2, warmup)):
+            net(*inp)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            net(*inp)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"record_len": rl, "agents_per_step": int(sum(rl)), "ms_per_step": ms,
+                "scenes_per_s": batch / (ms * 1e-3), "agents_per_s": sum(rl) / (ms * 1e-3)}
+    except Exception as e:      # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 # ---------------------------------------------------------------------------------------------
 def kernel_breakdown(pkg, net, inp, iters=3):
     """Per-kernel CUDA-event times of one forward, issued op by op through the same C-ABI entry points
@@ -359,6 +384,7 @@ def main():
         stop.set()
         th.join(timeout=2)
         kern = kernel_breakdown(pkg, net, dev_in) if rank == 0 else None
+        ragged = ragged_variant(net, dev, Bq, args.steps, args.warmup) if rank == 0 and world == 1 else None
     train = None
     if not args.no_train:
         train = train_step_bench(pkg, dev, dist, world, rank, Bq, steps=max(2, min(args.steps, 5)))
@@ -448,6 +474,8 @@ def main():
                                                 "last stage's chain launch, so the per-kernel sum exceeds the step by about this entry")
     if train is not None:
         line["train_step"] = train
+    if ragged is not None:
+        line["ragged_variant"] = ragged
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(2, 1)
     elif world == 1:
