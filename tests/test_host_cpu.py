@@ -113,3 +113,18 @@ def test_launch_accounting():
     assert ops.fusion_launch_count(2, True, skip_dead=True) == 16
     assert ops.fusion_launch_count(1, True) == 8
 
+
+
+def test_bench_flop_count_matches_survey():
+    """190.5 GFLOP per config-2 scene with all agents as queries; with last-stage dead-query
+    elimination (Lv-1)/Lv of that stage's Q projection, QK^T, PV, O and FFN terms are subtracted."""
+    import importlib.util
+    import os
+    sp = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(__file__), "..", "bench.py"))
+    b = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(b)
+    assert abs(b.scene_flops(5) / 1e9 - 190.455) < 1e-3
+    N, C, Lv = 8448, 256, 5
+    skipped = (Lv - 1) * N * (2 * C * C + 2 * (Lv * 64) * 2 * C + 2 * C * C + 4 * C * C)
+    assert b.scene_flops(5, 2, True) == b.scene_flops(5) - skipped
+    assert abs(b.scene_flops(2) / 1e9 - 64.2) < 0.1                      # config 1 figure of the survey
