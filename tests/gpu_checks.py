@@ -260,6 +260,18 @@ def check_mask_adversarial():
     mo = O.roi_and_cav_mask((B, L, H, W, 1), cav, T, 0.4, 4)
     res = {"tie_pose_mismatch_vs_oracle": int((m != mo).sum()), "pixels": int(m.numel())}
     assert res["tie_pose_mismatch_vs_oracle"] == 0, res
+    # the same pose families against the REFERENCE's own masks (tests/golden/mask_ties.npz, made by
+    # tests/golden/make_golden_ties.py): whole-cell shifts bit-exact; half-cell shifts (every coordinate an exact
+    # rounding tie, decided by the reference's fp32 round-off) counted -- see test_oracle_golden.py for the tie proof
+    g = np.load(os.path.join(GOLDEN, "mask_ties.npz"))
+    n = int(np.prod(g["shape"]))
+    for name in ("whole_cell", "half_cell"):
+        Tg = torch.from_numpy(g[name + "_T"])
+        ref = torch.from_numpy(np.unpackbits(g[name])[:n].reshape(B, H, W, 1, L)).float()
+        mg = p.get_roi_and_cav_mask((B, L, H, W, 1), cav.to(DEV), Tg.to(DEV), 0.4, 4).cpu()
+        assert int((mg != O.roi_and_cav_mask((B, L, H, W, 1), cav, Tg, 0.4, 4)).sum()) == 0, name
+        res[name + "_mismatch_vs_reference"] = int((mg != ref).sum())
+    assert res["whole_cell_mismatch_vs_reference"] == 0 and res["half_cell_mismatch_vs_reference"] <= n // 100, res
     return res
 
 
