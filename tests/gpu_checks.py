@@ -378,12 +378,21 @@ def check_fusion_config5_scene():
     return res
 
 
+def _vs_reference_sample(name, y):
+    """rel-L2 of the fused feature against the REFERENCE's own output at the BASELINE config shapes (strided sample,
+    tests/golden/fusion_configs.npz made by tests/golden/make_golden_configs.py from the same seeded inputs)."""
+    g = np.load(os.path.join(GOLDEN, "fusion_configs.npz"))
+    sc, sh, sw = (int(v) for v in g["strides"])
+    return rel_l2(y[:, ::sc, ::sh, ::sw], torch.from_numpy(g[name + "_sample"]))
+
+
 def check_fusion_config1():
     """BASELINE config 1: 2 agents (LiDAR ego + camera collaborator), 256x48x176, batch 1."""
     cfg, P, inp, y, net = _fusion_case(1, 2, 48, 176, [2], seed=1235, mode=[[1, 0]])
     ref = O.hetero_fusion(*inp, P, cfg)
-    res = {"rel_l2_vs_oracle": rel_l2(y, ref), "max_rel_vs_oracle": max_rel(y, ref)}
-    assert res["rel_l2_vs_oracle"] < 1e-3, res
+    res = {"rel_l2_vs_oracle": rel_l2(y, ref), "max_rel_vs_oracle": max_rel(y, ref),
+           "rel_l2_vs_reference_sample": _vs_reference_sample("config1", y)}
+    assert res["rel_l2_vs_oracle"] < 1e-3 and res["rel_l2_vs_reference_sample"] < 1e-3, res
     return res
 
 
@@ -391,8 +400,9 @@ def check_fusion_config2_scene():
     """BASELINE config 2 shape, one scene (5 mixed agents, 48x176) + ragged second scene."""
     cfg, P, inp, y, net = _fusion_case(2, 5, 48, 176, [5, 3], seed=1236)
     ref = O.hetero_fusion(*inp, P, cfg)
-    res = {"rel_l2_vs_oracle": rel_l2(y, ref), "max_rel_vs_oracle": max_rel(y, ref)}
-    assert res["rel_l2_vs_oracle"] < 1e-3, res
+    res = {"rel_l2_vs_oracle": rel_l2(y, ref), "max_rel_vs_oracle": max_rel(y, ref),
+           "rel_l2_vs_reference_sample": _vs_reference_sample("config2_scene", y)}
+    assert res["rel_l2_vs_oracle"] < 1e-3 and res["rel_l2_vs_reference_sample"] < 1e-3, res
     # exact dead-query elimination: same result without it, up to nothing (identical kernels on slot 0)
     net.skip_dead_queries = False
     x, T, md, rl, mask = inp

@@ -168,3 +168,24 @@ def test_mask_adversarial_poses_vs_reference_golden():
     assert float(tie.max()) < 1e-6                       # the poses really are all-tie
     assert int(diff.sum()) <= n // 100, int(diff.sum())
     assert float(tie[diff].max()) < 1e-6 if diff.any() else True
+
+
+@pytest.mark.parametrize("name,B,L,rl,seed,mode", [("config1", 1, 2, [2], 1235, [[1, 0]]),
+                                                   ("config2_scene", 2, 5, [5, 3], 1236, None)])
+def test_oracle_vs_reference_at_config_shapes(name, B, L, rl, seed, mode):
+    """BASELINE configs[0] (2 agents, LiDAR ego + camera collaborator) and the configs[1] scene shape (5 mixed agents
+    + a ragged scene) at the full 256x48x176 map: the oracle against the reference's own output (strided sample and
+    whole-tensor norms, tests/golden/fusion_configs.npz from make_golden_configs.py)."""
+    g = np.load(os.path.join(GOLDEN, "fusion_configs.npz"))
+    sc, sh, sw = (int(v) for v in g["strides"])
+    cfg = O.default_config()
+    P = O.synth_state_dict(cfg, 0)
+    x, T, md, record_len, mask = O.synth_inputs(B, L, 256, 48, 176, rl, seed, mode=mode)
+    assert checksum(x) == pytest.approx(float(g[name + "_in_checksum"][0]), rel=1e-9)
+    assert checksum(T) == pytest.approx(float(g[name + "_in_checksum"][1]), rel=1e-9)
+    with torch.no_grad():
+        y = O.hetero_fusion(x, T, md, record_len, mask, P, cfg)
+    ref = torch.from_numpy(g[name + "_sample"])
+    assert rel_l2(y[:, ::sc, ::sh, ::sw], ref) < 1e-5
+    assert float(y.double().norm()) == pytest.approx(float(g[name + "_norms"][0]), rel=1e-5)
+    assert float(y.double().abs().sum()) == pytest.approx(float(g[name + "_norms"][1]), rel=1e-5)
