@@ -120,3 +120,43 @@ def test_training_mode_dropout_is_rejected_and_cpu_tensors_raise():
     x, T, m, rl, mask = inp
     with pytest.raises(ValueError):
         net.eval()(x.requires_grad_(True), T, m, rl, mask)               # CPU tensors: no fallback
+
+
+def test_gradients_match_reference_autograd_golden():
+    """The same case against autograd through the REFERENCE itself (tests/golden/grads_c256.npz, made by
+    tests/golden/make_golden_grads.py): dL/dx (strided sample + norm), every parameter gradient (norm + 64-value
+    sample), and the set of parameters that receive no gradient -- for the oracle's autograd AND for the product's
+    backward orchestration (training.fusion_train over the exact-fp32 kernel restatements)."""
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "grads_c256.npz"))
+    pkg, cfg, P, net, inp = _setup(2, 3, 16, 24, [3, 2], seed=11)
+    x, T, m, rl, mask = inp
+    g_out = torch.randn(2, 256, 16, 24, generator=torch.Generator().manual_seed(3))
+    names = [str(n) for n in g["names"]]
+    nograd = {str(n) for n in g["nograd"]}
+    dx_ref = torch.from_numpy(g["dx_sample"])
+    samples = torch.from_numpy(g["samples"])
+
+    def compare(dx, grads, tol_x, tol_p):
+        assert _rel(dx[:, :, ::8, ::2, ::2], dx_ref) < tol_x
+        assert float(dx.double().norm()) == pytest.approx(float(g["dx_norm"][0]), rel=tol_x)
+        for k, name in enumerate(names):
+            gr = grads[name]
+            assert gr is not None, name
+            flat = gr.reshape(-1)
+            idx = torch.linspace(0, flat.numel() - 1, 64).long()
+            assert float(flat.double().norm()) == pytest.approx(float(g["norms"][k]), rel=tol_p), name
+            assert float((flat[idx] - samples[k]).norm()) <= tol_p * float(g["norms"][k]), name
+        for name in nograd:
+            gr = grads.get(name)
+            assert gr is None or float(gr.abs().max()) < 1e-6, name
+
+    y_o, g_o = _oracle_grads(cfg, P, inp, g_out)
+    assert float(y_o.double().norm()) == pytest.approx(float(g["y_norm"][0]), rel=1e-5)
+    compare(g_o["x"], g_o, 1e-4, 2e-4)
+
+    xg = x.clone().requires_grad_(True)
+    y = pkg.training.fusion_train(emul_ops, net.hetero_fusion_block, net, xg, T, m, rl, mask, num_iters=net.num_iters,
+                                  skip_dead=True)
+    (y * g_out).sum().backward()
+    compare(xg.grad, {n: p.grad for n, p in net.named_parameters()}, 2e-4, 5e-4)
