@@ -14,8 +14,8 @@ timeout 60 python __graft_entry__.py smoke > $out/${tag}_smoke.log 2>&1; echo "s
 timeout 240 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-train --no-cpu-baseline > $out/${tag}_ncu_b.log 2>&1
-# full-set capture of one forward's kernels (16 launches) after the warm-up launches
-timeout 300 ncu --set full --clock-control none --import-source on --launch-skip 64 -c 16 -o $out/${tag}_prof -f \
-    python bench.py --steps 2 --warmup 3 --no-train --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1
+# full-set capture of the forward's kernels after the first forward's launches (the command round 1's captures used)
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"warp_compact|dense_attn|qkv_kernel|chain_kernel" \
+    -s 16 -c 5 -o $out/${tag}_prof -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-train > $out/${tag}_ncu_full.log 2>&1
 tail -n 3 $out/${tag}_tests.log $out/${tag}_smoke.log
 head -c 600 $out/${tag}_bench.json; echo
