@@ -3,9 +3,10 @@ feature plus whole-tensor norms (the full tensors are 8.6 MB per scene -- too la
 
   config1        : B=1, L=2, mode [[1,0]] (LiDAR ego + camera collaborator), seed 1235  (BASELINE configs[0])
   config2_scene  : B=2, L=5, record_len [5,3], mixed modes, seed 1236               (configs[1] shape + a ragged scene)
+  config5_scene  : B=1, L=7, LiDAR ego + 6 camera collaborators, 256x96x352, seed 1239 (configs[4] stress shape, one scene)
 
 Inputs / parameters are the ones tests/gpu_checks.py regenerates (synth_state_dict seed 0, synth_inputs).
-Run in the build container only (needs /root/reference):  python tests/golden/make_golden_configs.py
+Run in the build container only (needs /root/reference):  python tests/golden/make_golden_configs.py [case ...]
 """
 import os
 import sys
@@ -21,16 +22,13 @@ import ref_import  # noqa: E402
 from oracle import hmvit_oracle as O  # noqa: E402
 
 CASES = {
-    # name: (B, L, record_len, seed, mode)
-    "config1": (1, 2, [2], 1235, [[1, 0]]),
-    "config2_scene": (2, 5, [5, 3], 1236, None),
+    # name: (B, L, record_len, seed, mode, H, W, synth_inputs kwargs, sample strides over (C, H, W))
+    "config1": (1, 2, [2], 1235, [[1, 0]], 48, 176, {}, (8, 4, 4)),
+    "config2_scene": (2, 5, [5, 3], 1236, None, 48, 176, {}, (8, 4, 4)),
+    # BASELINE configs[4] (stress) shape, one scene: LiDAR ego + 6 camera collaborators, 256x96x352 (~10 GB peak in the reference)
+    "config5_scene": (1, 7, [7], 1239, [[1, 0, 0, 0, 0, 0, 0]], 96, 352, {"tx": 100.0, "ty": 30.0}, (8, 8, 8)),
 }
-H, W, C = 48, 176, 256
-SC, SH, SW = 8, 4, 4            # sample strides over (C, H, W)
-
-
-def sample(y):
-    return y[:, ::SC, ::SH, ::SW].contiguous()
+C = 256
 
 
 def main():
@@ -40,15 +38,22 @@ def main():
     ref = R.HeteroFusion(cfg).eval()
     ref.load_state_dict(P, strict=True)
     out = {}
-    for name, (B, L, rl, seed, mode) in CASES.items():
-        x, T, md, record_len, mask = O.synth_inputs(B, L, C, H, W, rl, seed, mode=mode)
+    only = sys.argv[1:]
+    path = os.path.join(HERE, "fusion_configs.npz")
+    if only and os.path.exists(path):
+        out.update({k: v for k, v in np.load(path).items() if k != "strides"})
+    for name, (B, L, rl, seed, mode, H, W, kw, (SC, SH, SW)) in CASES.items():
+        if only and name not in only:
+            continue
+        x, T, md, record_len, mask = O.synth_inputs(B, L, C, H, W, rl, seed, mode=mode, **kw)
         with torch.no_grad():
             y = ref(x.clone(), T.clone(), md.clone(), record_len.clone(), mask.clone())
-        out[name + "_sample"] = sample(y).numpy()
+        out[name + "_sample"] = y[:, ::SC, ::SH, ::SW].contiguous().numpy()
+        out[name + "_strides"] = np.array([SC, SH, SW])
         out[name + "_norms"] = np.array([float(y.double().norm()), float(y.double().abs().sum())])
         out[name + "_in_checksum"] = np.array([float(x.double().abs().sum()), float(T.double().abs().sum())])
         print(name, tuple(y.shape), out[name + "_norms"])
-    np.savez_compressed(os.path.join(HERE, "fusion_configs.npz"), strides=np.array([SC, SH, SW]), **out)
+    np.savez_compressed(path, strides=np.array([8, 4, 4]), **out)          # "strides": config1 / config2_scene (kept for the GPU helper)
 
 
 if __name__ == "__main__":

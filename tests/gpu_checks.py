@@ -373,8 +373,9 @@ def check_fusion_config5_scene():
     """BASELINE config 5 shape, one scene: 7 agents (LiDAR ego + 6 camera collaborators), 256x96x352."""
     cfg, P, inp, y, net = _fusion_case(1, 7, 96, 352, [7], seed=1239, mode=[[1, 0, 0, 0, 0, 0, 0]], tx=100.0, ty=30.0)
     ref = O.hetero_fusion(*inp, P, cfg)
-    res = {"rel_l2_vs_oracle": rel_l2(y, ref), "max_rel_vs_oracle": max_rel(y, ref)}
-    assert res["rel_l2_vs_oracle"] < 1e-3, res
+    res = {"rel_l2_vs_oracle": rel_l2(y, ref), "max_rel_vs_oracle": max_rel(y, ref),
+           "rel_l2_vs_reference_sample": _vs_reference_sample("config5_scene", y)}
+    assert res["rel_l2_vs_oracle"] < 1e-3 and res["rel_l2_vs_reference_sample"] < 1e-3, res
     return res
 
 
@@ -382,7 +383,7 @@ def _vs_reference_sample(name, y):
     """rel-L2 of the fused feature against the REFERENCE's own output at the BASELINE config shapes (strided sample,
     tests/golden/fusion_configs.npz made by tests/golden/make_golden_configs.py from the same seeded inputs)."""
     g = np.load(os.path.join(GOLDEN, "fusion_configs.npz"))
-    sc, sh, sw = (int(v) for v in g["strides"])
+    sc, sh, sw = (int(v) for v in g[name + "_strides"])
     return rel_l2(y[:, ::sc, ::sh, ::sw], torch.from_numpy(g[name + "_sample"]))
 
 

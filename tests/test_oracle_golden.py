@@ -170,17 +170,20 @@ def test_mask_adversarial_poses_vs_reference_golden():
     assert float(tie[diff].max()) < 1e-6 if diff.any() else True
 
 
-@pytest.mark.parametrize("name,B,L,rl,seed,mode", [("config1", 1, 2, [2], 1235, [[1, 0]]),
-                                                   ("config2_scene", 2, 5, [5, 3], 1236, None)])
-def test_oracle_vs_reference_at_config_shapes(name, B, L, rl, seed, mode):
-    """BASELINE configs[0] (2 agents, LiDAR ego + camera collaborator) and the configs[1] scene shape (5 mixed agents
-    + a ragged scene) at the full 256x48x176 map: the oracle against the reference's own output (strided sample and
-    whole-tensor norms, tests/golden/fusion_configs.npz from make_golden_configs.py)."""
+@pytest.mark.parametrize("name,B,L,rl,seed,mode,H,W,kw", [
+    ("config1", 1, 2, [2], 1235, [[1, 0]], 48, 176, {}),
+    ("config2_scene", 2, 5, [5, 3], 1236, None, 48, 176, {}),
+    ("config5_scene", 1, 7, [7], 1239, [[1, 0, 0, 0, 0, 0, 0]], 96, 352, {"tx": 100.0, "ty": 30.0})])
+def test_oracle_vs_reference_at_config_shapes(name, B, L, rl, seed, mode, H, W, kw):
+    """BASELINE configs[0] (2 agents, LiDAR ego + camera collaborator), the configs[1] scene shape (5 mixed agents
+    + a ragged scene) at the full 256x48x176 map and one scene of the configs[4] stress shape (7 agents, 256x96x352):
+    the oracle against the reference's own output (strided sample and whole-tensor norms,
+    tests/golden/fusion_configs.npz from make_golden_configs.py)."""
     g = np.load(os.path.join(GOLDEN, "fusion_configs.npz"))
-    sc, sh, sw = (int(v) for v in g["strides"])
+    sc, sh, sw = (int(v) for v in g[name + "_strides"])
     cfg = O.default_config()
     P = O.synth_state_dict(cfg, 0)
-    x, T, md, record_len, mask = O.synth_inputs(B, L, 256, 48, 176, rl, seed, mode=mode)
+    x, T, md, record_len, mask = O.synth_inputs(B, L, 256, H, W, rl, seed, mode=mode, **kw)
     assert checksum(x) == pytest.approx(float(g[name + "_in_checksum"][0]), rel=1e-9)
     assert checksum(T) == pytest.approx(float(g[name + "_in_checksum"][1]), rel=1e-9)
     with torch.no_grad():
