@@ -93,8 +93,8 @@ def clocks_summary(samples):
 # ---------------------------------------------------------------------------------------------
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full
-    capture of this same command (profiles/r1_traffic.json, written by tools/ncu_traffic.py); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    capture of this same command (profiles/r2_traffic.json, written by tools/ncu_traffic.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(path):
         return None
     return json.load(open(path)).get(kernel, {}).get("dram_bytes_per_launch")
@@ -189,11 +189,9 @@ def kernel_breakdown(pkg, net, inp, iters=3):
     cell = float(blk.discrete_ratio) * float(blk.downsample_rate)
     common = dict(B=Bq, L=L, N=N_TOK, mode=mode, record_len=rl)
     acc = {}
-    split_phase = None
-    if os.environ.get("HMVIT_ATTN_SPLIT", "1") != "0" and os.environ.get("HMVIT_ATTN_IMPL", "mma") != "tc":
-        import ctypes
-        split_phase = lib.load().hmvit_debug_split_phase
-        split_phase.argtypes = [ctypes.c_int]
+    # key records of the two partition kinds: computed once per forward (the first attention call of each kind writes
+    # them into its own workspace, the later calls reuse them -- what hmvit_fusion_forward does in one launch)
+    rec_ws = [torch.empty(max(ops.attn_workspace_bytes(Bq, L, H, W), 256), dtype=torch.uint8, device=dev) for _ in range(2)]
 
     def timed(name, fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -213,16 +211,13 @@ def kernel_breakdown(pkg, net, inp, iters=3):
                 timed("ln_qkv_gemm", lambda: ops.rowgemm(lib.GEMM_QKV, n_out=1280, a=xsrc, w0=w["wqkv0"], w1=w["wqkv1"],
                                                          bias=w["bqkv"], out=qkv, ego_only=dead,
                                                          ln_stats=None if (it == 0 and kind == 0) else stats, **common))
-                attn = lambda: ops.group_attn(B=Bq, L=L, H=H, W=W, kind=kind, mode=mode, record_len=rl,   # noqa: E731
-                                              cav_mask=cav, T=T, cell=cell, q=qkv[0], k=qkv[1:3], v=qkv[3:5],
-                                              bk=w["bk"], bv=w["bv"], bias_table=w["bias_table"], out=att,
-                                              ego_only=dead)
-                timed("group_attn", attn)
-                if split_phase is not None:
-                    # the two launches of the split attention on their own (same inputs; results discarded)
-                    split_phase(1); timed("group_attn/warp_compact", attn)
-                    split_phase(2); timed("group_attn/dense_attn", attn)
-                    split_phase(0)
+                attn = lambda valid: ops.group_attn(B=Bq, L=L, H=H, W=W, kind=kind, mode=mode, record_len=rl,   # noqa: E731
+                                                    cav_mask=cav, T=T, cell=cell, q=qkv[0], k=qkv[1:3], v=qkv[3:5],
+                                                    bk=w["bk"], bv=w["bv"], bias_table=w["bias_table"], out=att,
+                                                    ego_only=dead, workspace=rec_ws[kind], records_valid=valid)
+                if it == 0:
+                    timed("group_attn/with_record_pass", lambda: attn(False))   # record pass + attention (first use of a kind)
+                timed("group_attn", lambda: attn(True))
                 timed("out_ffn_chain", lambda: ops.out_ffn_chain(o=att, resid=xsrc, out=xres, wa0=w["wa0"], wa1=w["wa1"], ba=w["ba"],
                                                                  w1_0=w["w1h_0"], w1_1=w["w1h_1"], b1=w["b1"], w2_0=w["w2h_0"],
                                                                  w2_1=w["w2h_1"], b2=w["b2"], ego_only=dead, stats_out=stats,
@@ -433,16 +428,10 @@ def main():
         per_dead = (2 * Lv + 2) * N_TOK * C * 2 * Bq
         alg = (per_full * (launches - 1) + per_dead) / launches if net.skip_dead_queries else per_full
         achieved = alg / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
-        if sub:
-            tr = [ncu_traffic("warp_compact_kernel"), ncu_traffic("dense_attn_kernel")]
-            traffic = sum(tr) if all(t is not None for t in tr) else None
-            note = ("algorithmic bytes = Q + K' + V' read once + O written, bf16 (DESIGN.md), over the attention step = "
-                    "two launches (warp_compact_kernel + dense_attn_kernel, times summed; traffic = both launches: the "
-                    "compacted key tiles make a round trip through HBM); tensor work 2*2*Lv*N*(Lv*64)*2C FLOP per scene")
-        else:
-            traffic = ncu_traffic("group_attn_kernel")
-            note = ("algorithmic bytes = Q + K' + V' read once + O written, bf16 (DESIGN.md); the kernel is "
-                    "gather (L2->SM) bound, its tensor work is 2*2*Lv*N*(Lv*64)*2C FLOP per scene")
+        traffic = ncu_traffic("fused_attn_kernel")
+        note = ("algorithmic bytes = Q + K' + V' read once + O written, bf16 (DESIGN.md); one persistent tcgen05 kernel "
+                "(fused_attn_kernel) per stage, the blended key / value tiles stay in shared memory; the key-record pass "
+                "(tap_records_kernel) runs once per forward, not per stage; tensor work 2*2*Lv*N*(Lv*64)*2C FLOP per scene")
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                 "traffic": traffic, "peak_source": src, "note": note}
     else:
@@ -477,8 +466,13 @@ def main():
         "kernels": {k: {"ms_per_step": round(v["ms_per_step"], 4), "launches_per_step": v["launches_per_step"],
                         "share": round(v["ms_per_step"] / total_kernel_ms, 4)} for k, v in kern.items()},
     }
-    if sub:
-        line["kernels"]["group_attn"]["launches"] = {k.split("/")[1]: round(v["ms_per_step"], 4) for k, v in sub.items()}
+    if "group_attn/with_record_pass" in sub:
+        # record pass = (attention incl. its record pass) - (attention on valid records), over the two kinds of a forward
+        wr = sub["group_attn/with_record_pass"]
+        line["kernels"]["attn_records"] = {"ms_per_step": round(max(wr["ms_per_step"] - wr["launches_per_step"] * kern["group_attn"]["ms_per_step"]
+                                                                    / kern["group_attn"]["launches_per_step"], 0.0), 4),
+                                           "launches_per_step": 1,
+                                           "note": "both partition kinds in one launch inside hmvit_fusion_forward; estimated here by difference"}
     if net.skip_dead_queries and "head_gemm" in line["kernels"]:
         line["kernels"]["head_gemm"]["note"] = ("timed stand-alone (hmvit_ffn_head); inside hmvit_fusion_forward the head runs in the "
                                                 "last stage's chain launch, so the per-kernel sum exceeds the step by about this entry")

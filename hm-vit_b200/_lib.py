@@ -11,11 +11,13 @@ LIB_PATH = os.environ.get("HMVIT_LIB", os.path.join(_HERE, "libhmvit_b200.so")) 
 
 GEMM_QKV, GEMM_OUT, GEMM_FFN1, GEMM_FFN2, GEMM_HEAD1, GEMM_HEAD2, GEMM_QKV_NOLN = range(7)
 GEMM_LN_LIN_CM, GEMM_LIN_CM, GEMM_LIN_ROWS, GEMM_ROWS_LIN_CM = range(7, 11)
+ATTN_FUSED, ATTN_SPLIT, ATTN_SINGLE = range(3)     # HmvitAttnArgs.impl
+ABI_VERSION = 5
 
 EXPORTS = (
     "hmvit_abi_version", "hmvit_last_error", "hmvit_rowgemm", "hmvit_group_attn", "hmvit_warp_bilinear",
     "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
-    "hmvit_debug_probe", "hmvit_out_ffn_chain", "hmvit_ffn_head",
+    "hmvit_out_ffn_chain", "hmvit_ffn_head",
     "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
     "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes",
 )
@@ -45,7 +47,7 @@ class HeadArgs(C.Structure):
 
 class AttnArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("kind", C.c_int32), ("ego_only", C.c_int32),
+                ("kind", C.c_int32), ("ego_only", C.c_int32), ("impl", C.c_int32), ("records_valid", C.c_int32),
                 ("mode", C.c_void_p), ("record_len", C.c_void_p), ("cav_mask", C.c_void_p), ("T", C.c_void_p),
                 ("cell", C.c_double), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
                 ("bk", C.c_void_p), ("bv", C.c_void_p), ("bias_table", C.c_void_p), ("key_mask", C.c_void_p),
@@ -86,7 +88,7 @@ class FusionArgs(C.Structure):
                 ("stage", StageWeights * 2),
                 ("head_w1", C.c_void_p * 2), ("head_b1", C.c_void_p), ("head_w2", C.c_void_p * 2), ("head_b2", C.c_void_p),
                 ("xres", C.c_void_p), ("workspace", C.c_void_p), ("out", C.c_void_p),
-                ("head_w1h", C.c_void_p * 2), ("head_w2h", C.c_void_p * 2)]
+                ("head_w1h", C.c_void_p * 2), ("head_w2h", C.c_void_p * 2), ("attn_impl", C.c_int32)]
 
 
 _lib = None
@@ -112,7 +114,7 @@ def load():
     lib.hmvit_ffn_head.restype = C.c_int
     lib.hmvit_group_attn.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     lib.hmvit_group_attn.restype = C.c_int
-    lib.hmvit_group_attn_workspace_bytes.argtypes = [C.c_int32] * 4
+    lib.hmvit_group_attn_workspace_bytes.argtypes = [C.c_int32] * 5
     lib.hmvit_group_attn_workspace_bytes.restype = C.c_size_t
     lib.hmvit_warp_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_double, C.c_void_p]
@@ -120,14 +122,12 @@ def load():
     lib.hmvit_roi_cav_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_double, C.c_void_p]
     lib.hmvit_roi_cav_mask.restype = C.c_int
-    lib.hmvit_fusion_workspace_bytes.argtypes = [C.c_int32] * 4
+    lib.hmvit_fusion_workspace_bytes.argtypes = [C.c_int32] * 6
     lib.hmvit_fusion_workspace_bytes.restype = C.c_size_t
     lib.hmvit_fusion_forward.argtypes = [C.POINTER(FusionArgs), C.c_void_p]
     lib.hmvit_fusion_forward.restype = C.c_int
-    lib.hmvit_fusion_launch_count.argtypes = [C.c_int32, C.c_int32]
+    lib.hmvit_fusion_launch_count.argtypes = [C.c_int32, C.c_int32, C.c_int32]
     lib.hmvit_fusion_launch_count.restype = C.c_int
-    lib.hmvit_debug_probe.argtypes = [C.c_void_p, C.c_void_p]
-    lib.hmvit_debug_probe.restype = C.c_int
     i32, vp = C.c_int32, C.c_void_p
     lib.hmvit_bwd_row_stats.argtypes = [vp, vp, i32, i32, i32, vp, i32, C.c_float, vp]
     lib.hmvit_bwd_layernorm.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, i32, vp]
@@ -139,7 +139,7 @@ def load():
     for fn in ("hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
                "hmvit_bwd_wgrad", "hmvit_group_attn_bwd"):
         getattr(lib, fn).restype = C.c_int
-    if lib.hmvit_abi_version() != 4:
+    if lib.hmvit_abi_version() != ABI_VERSION:
         raise ImportError("libhmvit_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -3,14 +3,12 @@
 #include "../../include/hmvit_b200.h"
 #include "rowgemm.cuh"
 #include "attn.cuh"
-#include "attn_tc.cuh"
 #include "attn_split.cuh"
-#include "attn_dense_tc.cuh"
+#include "attn_fused.cuh"
 #include "attn_bwd.cuh"
 #include "bwd.cuh"
 #include "chain.cuh"
 #include "qkv.cuh"
-#include "probe.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -266,65 +264,117 @@ extern "C" int hmvit_ffn_head(const HmvitHeadArgs* a, void* stream) {
 // ------------------------------------------------------------------------------------------------
 // attention
 // ------------------------------------------------------------------------------------------------
-#ifndef HMVIT_DENSE_TC_DEFAULT
-#define HMVIT_DENSE_TC_DEFAULT 0
-#endif
-// timing aid: 1 = only the warp + compaction pass, 2 = only the dense attention pass (on tiles left by an earlier call)
-static int g_split_phase = 0;
-extern "C" int hmvit_debug_split_phase(int phase) { g_split_phase = phase; return HMVIT_OK; }
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-extern "C" size_t hmvit_group_attn_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W) {
+// key records of ONE partition kind: [B*L][G][L*64] KeyRec + [B*L][G] visible-key counts
+static size_t records_bytes(int B, int L, int H, int W) {
   const size_t G = static_cast<size_t>(H / 8) * (W / 8), BL = static_cast<size_t>(B) * L;
-  size_t bytes = 2 * BL * G * L * 2 * kBlobBytes;        // compacted key / value tiles (worst case: every key visible)
-  bytes += (BL * G * 4 + 255) / 256 * 256;               // visible-key counts
-  bytes += (BL * G * L * 64 + 255) / 256 * 256;          // key slots
-  return bytes;
+  return align_up(BL * G * L * kS * sizeof(KeyRec), 256) + align_up(BL * G * sizeof(int), 256);
+}
+// compacted key / value tiles of the split form (worst case: every key visible) + counts + key slots
+static size_t split_bytes(int B, int L, int H, int W) {
+  const size_t G = static_cast<size_t>(H / 8) * (W / 8), BL = static_cast<size_t>(B) * L;
+  return 2 * BL * G * L * 2 * kBlobBytes + align_up(BL * G * 4, 256) + align_up(BL * G * L * 64, 256);
+}
+static bool fused_applicable(int B, int L) { return L <= kRecMaxL && B * L <= kFusedMaxAgents; }
+
+extern "C" size_t hmvit_group_attn_workspace_bytes(int32_t impl, int32_t B, int32_t L, int32_t H, int32_t W) {
+  if (B <= 0 || L <= 0 || H <= 0 || W <= 0) return 0;
+  if (impl == HMVIT_ATTN_FUSED) return fused_applicable(B, L) ? records_bytes(B, L, H, W) : 0;
+  if (impl == HMVIT_ATTN_SPLIT) return L <= kSplitMaxL ? split_bytes(B, L, H, W) : 0;
+  return 0;
 }
 
-extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
+static int fill_attn_params(const HmvitAttnArgs* a, AttnParams& p) {
   HMVIT_CHECK_ARG(a != nullptr, "group_attn: null args");
   HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->H > 0 && a->W > 0, "group_attn: bad shape");
   HMVIT_CHECK_ARG(a->H % 8 == 0 && a->W % 8 == 0, "group_attn: H and W must be divisible by the window size 8");
   HMVIT_CHECK_ARG(a->B * a->L <= 65535, "group_attn: B*L exceeds grid limit");
   HMVIT_CHECK_ARG(a->kind == 0 || a->kind == 1, "group_attn: kind must be 0 (window) or 1 (grid)");
-  HMVIT_CHECK_ARG(a->mode && a->record_len && a->cav_mask && a->T && a->q && a->k && a->v && a->bk && a->bv &&
-                  a->bias_table && a->out, "group_attn: null pointer");
+  HMVIT_CHECK_ARG(a->mode && a->record_len && a->cav_mask && a->T, "group_attn: null pointer");
   HMVIT_CHECK_ARG(a->cell > 0.0, "group_attn: cell size must be positive");
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  // Two implementations of the same contract: the mma.sync kernel (attn.cuh, 4 CTAs / SM, every warp gathers and
-  // computes) is the default -- it is the faster one today (0.74 vs 1.0 ms per launch at config 2); the
-  // warp-specialised tcgen05 / TMEM kernel (attn_tc.cuh) is selected with HMVIT_ATTN_IMPL=tc and is kept
-  // parity-tested (profiles/r1_attention_study.md explains what bounds it).
-  static bool legacy = true;
-  static bool dense_tc = false;      // HMVIT_DENSE_IMPL=tc: second launch of the split form on tcgen05 (attn_dense_tc.cuh)
-  std::call_once(once, [] {
-    const char* impl = getenv("HMVIT_ATTN_IMPL");
-    legacy = !(impl != nullptr && strcmp(impl, "tc") == 0);
-    const char* dimpl = getenv("HMVIT_DENSE_IMPL");
-    dense_tc = HMVIT_DENSE_TC_DEFAULT ? !(dimpl != nullptr && strcmp(dimpl, "mma") == 0) : (dimpl != nullptr && strcmp(dimpl, "tc") == 0);
-    attr_err = cudaFuncSetAttribute(group_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(group_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnTcCfg::SMEM_BYTES);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(dense_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(dense_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DenseTcCfg::SMEM_BYTES);
-  });
-  HMVIT_CHECK_CUDA(attr_err);
-  AttnParams p;
   p.B = a->B; p.L = a->L; p.H = a->H; p.W = a->W; p.kind = a->kind; p.ego_only = a->ego_only ? 1 : 0;
   p.mode = a->mode; p.record_len = a->record_len; p.cav_mask = a->cav_mask; p.T = a->T; p.cell = a->cell;
   p.q = static_cast<const __nv_bfloat16*>(a->q); p.k = static_cast<const __nv_bfloat16*>(a->k);
   p.v = static_cast<const __nv_bfloat16*>(a->v); p.bk = a->bk; p.bv = a->bv; p.bias_table = a->bias_table; p.key_mask = a->key_mask;
   p.out = static_cast<__nv_bfloat16*>(a->out);
   p.lse = a->lse;
-  dim3 grid((a->H / 8) * (a->W / 8) * 2, a->B * a->L);      // x: (token group, head group)
-  if (a->workspace != nullptr && legacy) {
-    // split form: warp + compaction pass, then dense attention over the compacted key tiles
-    HMVIT_CHECK_ARG(a->L <= kSplitMaxL, "group_attn: the split form handles at most 8 agents per scene");
-    HMVIT_CHECK_ARG(a->workspace_bytes >= hmvit_group_attn_workspace_bytes(a->B, a->L, a->H, a->W), "group_attn: workspace too small");
+  return HMVIT_OK;
+}
+
+// tap / visibility records of `nkinds` partition kinds starting at kind0, laid out kind after kind in `ws`
+static int launch_records(const AttnParams& p, int kind0, int nkinds, void* ws, cudaStream_t st) {
+  const size_t G = static_cast<size_t>(p.H / 8) * (p.W / 8), BL = static_cast<size_t>(p.B) * p.L;
+  HMVIT_CHECK_ARG(p.L <= kRecMaxL, "attn_records: at most 8 agents per scene");
+  RecParams rp;
+  rp.a = p; rp.kind0 = kind0;
+  // records of all kinds first, then the counts of all kinds (fused_ws_split() below mirrors this)
+  rp.rec = static_cast<KeyRec*>(ws);
+  rp.nvis = reinterpret_cast<int*>(static_cast<uint8_t*>(ws) + nkinds * align_up(BL * G * p.L * kS * sizeof(KeyRec), 256));
+  dim3 grid(static_cast<unsigned>(G), static_cast<unsigned>(BL), nkinds);
+  tap_records_kernel<<<grid, 256, 0, st>>>(rp);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+static void fused_ws_split(const AttnParams& p, int nkinds, int which, void* ws, const KeyRec** rec, const int** nvis) {
+  const size_t G = static_cast<size_t>(p.H / 8) * (p.W / 8), BL = static_cast<size_t>(p.B) * p.L;
+  const size_t per_kind = BL * G * p.L * kS;
+  *rec = static_cast<const KeyRec*>(ws) + which * per_kind;
+  *nvis = reinterpret_cast<const int*>(static_cast<uint8_t*>(ws) + nkinds * align_up(per_kind * sizeof(KeyRec), 256)) + which * BL * G;
+}
+
+static int launch_fused_attn(const AttnParams& p, const KeyRec* rec, const int* nvis, cudaStream_t st) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(fused_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FaCfg::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(fused_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  FusedAttnParams fp;
+  fp.a = p; fp.rec = rec; fp.nvis = nvis;
+  const long long items = static_cast<long long>(p.B) * (p.ego_only ? 1 : p.L) * (p.H / 8) * (p.W / 8) * 2;
+  const long long cap = 2LL * num_sms();                       // 2 persistent CTAs per SM, one head group each
+  const int grid = static_cast<int>(items < cap ? items : cap);
+  fused_attn_kernel<<<grid, FaCfg::THREADS, FaCfg::SMEM_BYTES, st>>>(fp);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
+  AttnParams p;
+  int rc = fill_attn_params(a, p); if (rc) return rc;
+  HMVIT_CHECK_ARG(a->q && a->k && a->v && a->bk && a->bv && a->bias_table && a->out, "group_attn: null pointer");
+  HMVIT_CHECK_ARG(a->impl >= HMVIT_ATTN_FUSED && a->impl <= HMVIT_ATTN_SINGLE, "group_attn: unknown impl");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(group_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(dense_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  int impl = a->impl;
+  if (impl == HMVIT_ATTN_FUSED && !fused_applicable(a->B, a->L)) impl = HMVIT_ATTN_SINGLE;   // > 8 agents per scene
+  if (impl != HMVIT_ATTN_SINGLE) {
+    HMVIT_CHECK_ARG(a->workspace != nullptr, "group_attn: this implementation needs a workspace (hmvit_group_attn_workspace_bytes)");
+    HMVIT_CHECK_ARG(a->workspace_bytes >= hmvit_group_attn_workspace_bytes(impl, a->B, a->L, a->H, a->W), "group_attn: workspace too small");
     HMVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "group_attn: workspace must be 256-byte aligned");
+  }
+  if (impl == HMVIT_ATTN_FUSED) {
+    // persistent tcgen05 kernel fed by the key records of this partition kind (csrc/attn_fused.cuh)
+    if (!a->records_valid) { rc = launch_records(p, a->kind, 1, a->workspace, st); if (rc) return rc; }
+    const KeyRec* rec; const int* nvis;
+    fused_ws_split(p, 1, 0, a->workspace, &rec, &nvis);
+    return launch_fused_attn(p, rec, nvis, st);
+  }
+  dim3 grid((a->H / 8) * (a->W / 8) * 2, a->B * a->L);      // x: (token group, head group)
+  if (impl == HMVIT_ATTN_SPLIT) {
+    // warp + compaction pass, then mma.sync dense attention over the compacted key tiles (csrc/attn_split.cuh);
+    // kept as an independently written cross-check of the fused kernel
+    HMVIT_CHECK_ARG(a->L <= kSplitMaxL, "group_attn: the split form handles at most 8 agents per scene");
     const size_t G = static_cast<size_t>(a->H / 8) * (a->W / 8), BL = static_cast<size_t>(a->B) * a->L;
     SplitParams sp;
     sp.a = p;
@@ -334,19 +384,15 @@ extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
     sp.vc = ws; ws += tile_bytes;
     sp.nvis = reinterpret_cast<int*>(ws); ws += (BL * G * 4 + 255) / 256 * 256;
     sp.slots = ws;
-    sp.tc_layout = dense_tc ? 1 : 0;
+    sp.tc_layout = 0;
     dim3 grid_c(static_cast<unsigned>(G), a->B * a->L);
-    if (g_split_phase != 2) warp_compact_kernel<<<grid_c, kCompactThreads, 0, static_cast<cudaStream_t>(stream)>>>(sp);
+    warp_compact_kernel<<<grid_c, kCompactThreads, 0, st>>>(sp);
     HMVIT_CHECK_CUDA(cudaGetLastError());
-    if (g_split_phase != 1) {
-      if (dense_tc) dense_attn_tc_kernel<<<grid, DenseTcCfg::THREADS, DenseTcCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(sp);
-      else dense_attn_kernel<<<grid, kDenseThreads, kDenseSmem, static_cast<cudaStream_t>(stream)>>>(sp);
-    }
+    dense_attn_kernel<<<grid, kDenseThreads, kDenseSmem, st>>>(sp);
     HMVIT_CHECK_CUDA(cudaGetLastError());
     return HMVIT_OK;
   }
-  if (legacy || a->lse != nullptr) group_attn_kernel<<<grid, kAttnThreads, kAttnSmem, static_cast<cudaStream_t>(stream)>>>(p);
-  else group_attn_tc_kernel<<<grid, AttnTcCfg::THREADS, AttnTcCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
+  group_attn_kernel<<<grid, kAttnThreads, kAttnSmem, st>>>(p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }
@@ -421,85 +467,48 @@ extern "C" int hmvit_roi_cav_mask(const float* T, const int32_t* cav_mask, float
 // ------------------------------------------------------------------------------------------------
 // whole forward
 // ------------------------------------------------------------------------------------------------
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static int effective_attn_impl(int impl, int B, int L) {
+  if (impl == HMVIT_ATTN_FUSED && !fused_applicable(B, L)) return HMVIT_ATTN_SINGLE;
+  if (impl == HMVIT_ATTN_SPLIT && L > kSplitMaxL) return HMVIT_ATTN_SINGLE;
+  return impl;
+}
 
-extern "C" size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W) {
+extern "C" size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W, int32_t unfused, int32_t attn_impl) {
+  if (B <= 0 || L <= 0 || H <= 0 || W <= 0) return 0;
+  const int impl = effective_attn_impl(attn_impl, B, L);
   const size_t rows = static_cast<size_t>(B) * L * H * W;
   size_t bytes = 0;
   bytes += align_up(rows * 256 * 2 * 5, 1024);   // q, k|te0, k|te1, v|te0, v|te1 (bf16 rows)
   bytes += align_up(rows * 256 * 2, 1024);       // attention output (bf16 rows)
-  bytes += align_up(rows * 256 * 4, 1024);       // FFN hidden (fp32 cm, tf32 values; unfused path and head)
   bytes += align_up(rows * 2 * 4, 1024);         // per-row LayerNorm statistics handed from one stage to the next
-  if (L <= kSplitMaxL) bytes += align_up(hmvit_group_attn_workspace_bytes(B, L, H, W), 1024);   // compacted key / value tiles
+  if (unfused) bytes += align_up(rows * 256 * 4, 1024);   // FFN hidden (fp32 cm, tf32 values): unfused cross-check path only
+  if (impl == HMVIT_ATTN_FUSED) bytes += align_up(2 * records_bytes(B, L, H, W), 1024);   // key records of both partition kinds
+  if (impl == HMVIT_ATTN_SPLIT) bytes += align_up(split_bytes(B, L, H, W), 1024);         // compacted key / value tiles
   return bytes;
 }
 
-// HMVIT_ATTN_SPLIT=0 keeps the single-kernel attention inside the whole forward (A/B measurements).
-static bool split_attention() {
-  static bool on = [] { const char* e = getenv("HMVIT_ATTN_SPLIT"); return !(e != nullptr && e[0] == '0'); }();
-  return on;
-}
-
-// HMVIT_FUSE_HEAD=0 keeps the head as its own launch (A/B measurements).
-static bool fuse_head_enabled() {
-  static bool on = [] { const char* e = getenv("HMVIT_FUSE_HEAD"); return !(e != nullptr && e[0] == '0'); }();
-  return on;
-}
 static bool fuse_head(const HmvitFusionArgs* a) {
-  return fuse_head_enabled() && a->head && !a->unfused && a->skip_dead && a->head_w1h[0] && a->head_w1h[1] && a->head_w2h[0] &&
+  return a->head && !a->unfused && a->skip_dead && a->head_w1h[0] && a->head_w1h[1] && a->head_w2h[0] &&
          a->head_w2h[1] && a->head_b1 && a->head_b2 && a->out;
 }
 
 /* head: 0 = no head, 1 = head as its own launch, 2 = head with skip_dead (fused into the last stage's chain launch) */
-extern "C" int hmvit_fusion_launch_count(int32_t num_iters, int32_t head) {
-  const int head_launch = head == 0 ? 0 : ((head == 2 && fuse_head_enabled()) ? 0 : 1);
-  return num_iters * 2 * (split_attention() ? 4 : 3) + head_launch;
-}
-
-static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream);
-
-
-// Scenes are independent, so the forward can be issued scene chunk by scene chunk through all stages with
-// the same workspace (HMVIT_SCENE_CHUNK=n).  Measured on B200 at config 2: slower than one launch per stage
-// over the whole batch (wave quantisation of the persistent GEMM kernels outweighs the L2 residency), so
-// the default is the whole batch.
-static int scene_chunk() {
-  static int chunk = [] {
-    const char* e = getenv("HMVIT_SCENE_CHUNK");
-    const int v = e ? atoi(e) : 0;
-    return v > 0 ? v : (1 << 30);
-  }();
-  return chunk;
+extern "C" int hmvit_fusion_launch_count(int32_t num_iters, int32_t head, int32_t attn_impl) {
+  const int head_launch = head == 1 ? 1 : 0;
+  if (attn_impl == HMVIT_ATTN_FUSED) return 1 + num_iters * 2 * 3 + head_launch;   // key records (both kinds) + per stage {QKV, attention, chain}
+  return num_iters * 2 * (attn_impl == HMVIT_ATTN_SPLIT ? 4 : 3) + head_launch;
 }
 
 extern "C" int hmvit_fusion_forward(const HmvitFusionArgs* a, void* stream) {
-  HMVIT_CHECK_ARG(a != nullptr, "fusion_forward: null args");
-  HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->H > 0 && a->W > 0, "fusion_forward: bad shape");
-  const int chunk = scene_chunk();
-  const size_t per_scene = static_cast<size_t>(a->L) * 256 * a->H * a->W;
-  for (int b0 = 0; b0 < a->B; b0 += chunk) {
-    HmvitFusionArgs c = *a;
-    c.B = (a->B - b0 < chunk) ? (a->B - b0) : chunk;
-    c.x = a->x + b0 * per_scene;
-    c.T = a->T + static_cast<size_t>(b0) * a->L * a->L * 16;
-    c.mode = a->mode + b0 * a->L;
-    c.record_len = a->record_len + b0;
-    c.cav_mask = a->cav_mask + b0 * a->L;
-    c.xres = a->xres ? a->xres + b0 * per_scene : nullptr;
-    c.out = a->out ? a->out + static_cast<size_t>(b0) * 256 * a->H * a->W : nullptr;
-    int rc = fusion_forward_chunk(&c, stream);
-    if (rc) return rc;
-  }
-  return HMVIT_OK;
-}
-
-static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a != nullptr, "fusion_forward: null args");
   HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->H > 0 && a->W > 0, "fusion_forward: bad shape");
   HMVIT_CHECK_ARG(a->H % 8 == 0 && a->W % 8 == 0, "fusion_forward: H and W must be divisible by the window size 8");
   HMVIT_CHECK_ARG(a->num_iters >= 1, "fusion_forward: num_iters must be >= 1");
   HMVIT_CHECK_ARG(a->x && a->T && a->mode && a->record_len && a->cav_mask && a->xres && a->workspace, "fusion_forward: null pointer");
   HMVIT_CHECK_ARG(!a->head || a->out, "fusion_forward: out is null");
+  HMVIT_CHECK_ARG(a->cell > 0.0, "fusion_forward: cell size must be positive");
+  HMVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "fusion_forward: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int N = a->H * a->W;
   const size_t rows = static_cast<size_t>(a->B) * a->L * N;
   uint8_t* ws = static_cast<uint8_t*>(a->workspace);
@@ -507,13 +516,25 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
   ws += align_up(rows * 256 * 2 * 5, 1024);
   __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws);
   ws += align_up(rows * 256 * 2, 1024);
-  float* hid = reinterpret_cast<float*>(ws);
-  ws += align_up(rows * 256 * 4, 1024);
   float* stats = reinterpret_cast<float*>(ws);
   ws += align_up(rows * 2 * 4, 1024);
-  void* attn_ws = (a->L <= kSplitMaxL && split_attention()) ? ws : nullptr;
+  float* hid = nullptr;
+  if (a->unfused) { hid = reinterpret_cast<float*>(ws); ws += align_up(rows * 256 * 4, 1024); }
+  HMVIT_CHECK_ARG(a->attn_impl >= HMVIT_ATTN_FUSED && a->attn_impl <= HMVIT_ATTN_SINGLE, "fusion_forward: unknown attn_impl");
+  const int attn_impl = effective_attn_impl(a->attn_impl, a->B, a->L);
+  const bool fused_attn = attn_impl == HMVIT_ATTN_FUSED;
+  void* rec_ws = ws;                              // key records (fused) or compacted tiles (split)
   bool have_stats = false;                        // stats describe the rows currently in xres
   bool head_done = false;                         // the head ran inside the last stage's chain launch
+
+  AttnParams geo;
+  memset(&geo, 0, sizeof(geo));
+  geo.B = a->B; geo.L = a->L; geo.H = a->H; geo.W = a->W; geo.mode = a->mode; geo.record_len = a->record_len;
+  geo.cav_mask = a->cav_mask; geo.T = a->T; geo.cell = a->cell;
+  if (fused_attn) {
+    // the poses do not change between the block iterations: key records of both partition kinds, once per forward
+    int rc = launch_records(geo, 0, 2, rec_ws, st); if (rc) return rc;
+  }
 
   for (int it = 0; it < a->num_iters; ++it) {
     for (int kind = 0; kind < 2; ++kind) {
@@ -530,14 +551,25 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
       int rc = hmvit_rowgemm(HMVIT_GEMM_QKV, &g, stream); if (rc) return rc;
       g.ln_stats = nullptr;
       // warp + mask + attention
-      HmvitAttnArgs t;
-      memset(&t, 0, sizeof(t));
-      t.B = a->B; t.L = a->L; t.H = a->H; t.W = a->W; t.kind = kind; t.ego_only = dead;
-      t.mode = a->mode; t.record_len = a->record_len; t.cav_mask = a->cav_mask; t.T = a->T; t.cell = a->cell;
-      t.q = qkv; t.k = qkv + rows * 256; t.v = qkv + rows * 256 * 3; t.bk = w.bk; t.bv = w.bv; t.bias_table = w.bias_table;
-      t.out = att;
-      t.workspace = attn_ws; t.workspace_bytes = attn_ws ? hmvit_group_attn_workspace_bytes(a->B, a->L, a->H, a->W) : 0;
-      rc = hmvit_group_attn(&t, stream); if (rc) return rc;
+      HMVIT_CHECK_ARG(w.bk && w.bv && w.bias_table, "fusion_forward: attention biases missing");
+      AttnParams p = geo;
+      p.kind = kind; p.ego_only = dead;
+      p.q = qkv; p.k = qkv + rows * 256; p.v = qkv + rows * 256 * 3; p.bk = w.bk; p.bv = w.bv; p.bias_table = w.bias_table;
+      p.out = att;
+      if (fused_attn) {
+        const KeyRec* rec; const int* nvis;
+        fused_ws_split(geo, 2, kind, rec_ws, &rec, &nvis);
+        rc = launch_fused_attn(p, rec, nvis, st); if (rc) return rc;
+      } else {
+        // split / single cross-check forms, and shapes with more than 8 agents per scene (csrc/attn_split.cuh, attn.cuh)
+        HmvitAttnArgs t;
+        memset(&t, 0, sizeof(t));
+        t.B = a->B; t.L = a->L; t.H = a->H; t.W = a->W; t.kind = kind; t.ego_only = dead; t.impl = attn_impl;
+        if (attn_impl == HMVIT_ATTN_SPLIT) { t.workspace = rec_ws; t.workspace_bytes = split_bytes(a->B, a->L, a->H, a->W); }
+        t.mode = a->mode; t.record_len = a->record_len; t.cav_mask = a->cav_mask; t.T = a->T; t.cell = a->cell;
+        t.q = p.q; t.k = p.k; t.v = p.v; t.bk = w.bk; t.bv = w.bv; t.bias_table = w.bias_table; t.out = att;
+        rc = hmvit_group_attn(&t, stream); if (rc) return rc;
+      }
       if (a->unfused) {
         // output projection + residual
         g.n_out = 256; g.a = att; g.w[0] = w.wa[0]; g.w[1] = w.wa[1]; g.bias = w.ba; g.resid = xsrc; g.out = a->xres;
@@ -576,9 +608,9 @@ static int fusion_forward_chunk(const HmvitFusionArgs* a, void* stream) {
     }
   }
   if (a->head && !head_done) {
-    HMVIT_CHECK_ARG(a->head_w1[0] && a->head_w1[1] && a->head_w2[0] && a->head_w2[1] && a->head_b1 && a->head_b2,
-                    "fusion_forward: head weights missing");
+    HMVIT_CHECK_ARG(a->head_b1 && a->head_b2, "fusion_forward: head biases missing");
     if (a->unfused) {
+      HMVIT_CHECK_ARG(a->head_w1[0] && a->head_w1[1] && a->head_w2[0] && a->head_w2[1], "fusion_forward: head weights missing");
       HmvitRowGemmArgs g;
       memset(&g, 0, sizeof(g));
       g.B = a->B; g.L = a->L; g.N = N; g.mode = a->mode; g.record_len = a->record_len; g.ego_only = 1; g.ln_eps = a->ln_eps;
@@ -716,52 +748,10 @@ extern "C" int hmvit_group_attn_bwd(const HmvitAttnBwdArgs* a, void* stream) {
   return HMVIT_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-// diagnostics
-// ------------------------------------------------------------------------------------------------
-__global__ void debug_probe_kernel(uint32_t* out) {
-  extern __shared__ uint8_t dsm[];
-  __shared__ uint32_t slot;
-  if (threadIdx.x < 32) tmem_alloc<32>(&slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (threadIdx.x == 0) { out[0] = smem_u32(dsm) & 1023u; out[1] = slot; }
-  __syncthreads();
-  if (threadIdx.x < 32) tmem_dealloc<32>(slot);
-}
-extern "C" int hmvit_debug_probe(uint32_t* out2, void* stream) {
-  HMVIT_CHECK_ARG(out2 != nullptr, "debug_probe: null pointer");
-  debug_probe_kernel<<<1, 64, 1024, static_cast<cudaStream_t>(stream)>>>(out2);
-  HMVIT_CHECK_CUDA(cudaGetLastError());
-  return HMVIT_OK;
-}
-
-extern "C" int hmvit_debug_umma(const void* A, const void* Bm, float* D, int N, int b_mn_major, unsigned lbo, unsigned sbo,
-                                unsigned kstep_bytes, void* stream) {
-  HMVIT_CHECK_ARG(A && Bm && D, "debug_umma: null pointer");
-  HMVIT_CHECK_ARG(N >= 16 && N <= 128 && N % 16 == 0, "debug_umma: N must be 16..128, multiple of 16");
-  static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40960); });
-  umma_probe_kernel<<<1, 128, 16384 + 16384 + 1024, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(A), static_cast<const __nv_bfloat16*>(Bm), D, N, b_mn_major, lbo, sbo, kstep_bytes);
-  HMVIT_CHECK_CUDA(cudaGetLastError());
-  return HMVIT_OK;
-}
-
 #ifdef HMVIT_TS
-extern "C" int hmvit_debug_attn_ts(unsigned long long* host_out /* [8][8][4] */) {
-  HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_attn_ts, sizeof(unsigned long long) * 8 * 8 * 4));
-  return HMVIT_OK;
-}
-extern "C" int hmvit_debug_tc_ts(unsigned long long* host_out /* [8][3][64] */) {
-  HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_tc_ts, sizeof(unsigned long long) * 8 * 3 * 64));
-  return HMVIT_OK;
-}
-extern "C" int hmvit_debug_dtc_ts(unsigned long long* host_out /* [8][4][32] */) {
-  HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_dtc_ts, sizeof(unsigned long long) * 8 * 4 * 32));
-  return HMVIT_OK;
-}
+// ------------------------------------------------------------------------------------------------
+// timeline instrumentation (tools/build_variant.sh -DHMVIT_TS builds only; not part of the product library)
+// ------------------------------------------------------------------------------------------------
 extern "C" int hmvit_debug_qkv_ts(unsigned long long* host_out /* [3][512] */) {
   HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_qkv_ts, sizeof(unsigned long long) * 3 * 512));
   return HMVIT_OK;

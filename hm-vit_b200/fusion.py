@@ -116,6 +116,8 @@ def _stack2(fn):
 class HeteroAttention(nn.Module):
     """Parameters of the typed multi-agent attention (hetero_fusion.py:16-109) + the unit-level forward."""
 
+    attn_impl = None      # None: fused persistent tcgen05 attention; "split" / "single": cross-check forms (ops.group_attn)
+
     def __init__(self, dim, dim_head=32, dropout=0., agent_size=6, window_size=7, num_types=_NUM_TYPES):
         super().__init__()
         assert (dim % dim_head) == 0, 'dimension should be divisible by dimension per head'
@@ -215,7 +217,7 @@ class HeteroAttention(nn.Module):
         att = torch.zeros(rows, c, dtype=torch.bfloat16, device=dev)
         ops.group_attn(B=b, L=l, H=H, W=W, kind=0, mode=mode_i, record_len=rl, cav_mask=cav, T=T, cell=1.0,
                        q=qkv[0], k=qkv[1:3], v=qkv[3:5], bk=pk["bk"], bv=pk["bv"], bias_table=pk["bias_table"],
-                       out=att, ego_only=True, key_mask=km)
+                       out=att, ego_only=True, key_mask=km, impl=self.attn_impl)
         zero = torch.zeros(b, l, c, N, dtype=torch.float32, device=dev)
         out = torch.zeros(b, l, c, N, dtype=torch.float32, device=dev)
         ops.rowgemm(_lib.GEMM_OUT, B=b, L=l, N=N, n_out=c, mode=mode_i, record_len=rl, a=att,
@@ -265,6 +267,9 @@ def _check_inputs(block, x):
 class HeteroFusionBlock(nn.Module):
     """hetero_fusion.py:279-474 -- window stage then grid stage, each LN -> warp -> per-ego attention
     -> residual -> pre-norm FFN residual.  Only architect_mode == 'sequential' (the shipped yaml)."""
+
+    attn_impl = None      # attention implementation inside hmvit_fusion_forward (see HeteroAttention.attn_impl)
+    unfused_chain = False  # True: OUT / FFN1 / FFN2 as three row-GEMMs instead of the fused chain kernel (cross-check)
 
     def __init__(self, config):
         super().__init__()
@@ -429,14 +434,17 @@ def _run_fusion(block: HeteroFusionBlock, fusion, x, pairwise_t_matrix, mode, re
     head = fusion is not None
     if xres is None:
         xres = torch.empty_like(x)
-    ws = _workspace(ops.fusion_workspace_bytes(B, L, H, W), dev)
+    unfused = bool(block.unfused_chain)
+    attn_impl = block.attn_impl
+    ws = _workspace(ops.fusion_workspace_bytes(B, L, H, W, unfused, attn_impl), dev)
     out = torch.empty(B, Cc, H, W, dtype=torch.float32, device=dev) if head else None
 
     args = _lib.FusionArgs()
     args.B, args.L, args.H, args.W = B, L, H, W
     args.num_iters, args.head = num_iters, 1 if head else 0
     args.skip_dead = 1 if (head and fusion.skip_dead_queries) else 0
-    args.unfused = 1 if getattr(block, "unfused_chain", False) else 0
+    args.unfused = 1 if unfused else 0
+    args.attn_impl = ops._IMPL[attn_impl]
     args.x, args.T = x.data_ptr(), T.data_ptr()
     args.mode, args.record_len, args.cav_mask = mode_i.data_ptr(), rl.data_ptr(), cav.data_ptr()
     args.cell = float(block.discrete_ratio) * float(block.downsample_rate)

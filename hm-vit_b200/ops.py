@@ -4,7 +4,6 @@ torch is used for device memory and the current stream only; every arithmetic st
 path happens inside libhmvit_b200.so.  All tensors must be CUDA, contiguous.
 """
 import ctypes as C
-import os
 
 import torch
 
@@ -93,28 +92,35 @@ def ffn_head(*, B, L, N, mode, record_len, x, w1_0, w1_1, b1, w2_0, w2_1, b2, ou
 _ATTN_WS = {}
 
 
-def _attn_workspace(B, L, H, W, device):
-    """Scratch for the split attention (compacted key / value tiles), cached per shape and device."""
-    key = (B, L, H, W, str(device))
+def _attn_workspace(impl, B, L, H, W, device):
+    """Scratch of hmvit_group_attn (key records of the fused kernel / compacted tiles of the split form), cached per
+    implementation, shape and device."""
+    key = (impl, B, L, H, W, str(device))
     ws = _ATTN_WS.get(key)
     if ws is None:
         _ATTN_WS.clear()
-        nbytes = int(_lib.load().hmvit_group_attn_workspace_bytes(B, L, H, W))
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        nbytes = int(_lib.load().hmvit_group_attn_workspace_bytes(impl, B, L, H, W))
+        ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
         _ATTN_WS[key] = ws
     return ws
 
 
+_IMPL = {None: _lib.ATTN_FUSED, "fused": _lib.ATTN_FUSED, "split": _lib.ATTN_SPLIT, "single": _lib.ATTN_SINGLE}
+
+
 def group_attn(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, k, v, bk, bv, bias_table, out,
-               ego_only=False, key_mask=None, lse=None, split=None):
-    """split=None: the split form (warp + compaction pass, dense attention pass) whenever L <= 8 unless
-    HMVIT_ATTN_SPLIT=0; split=False: the single fused kernel."""
+               ego_only=False, key_mask=None, lse=None, impl=None, workspace=None, records_valid=False):
+    """impl: None / "fused" (default: key-record pass + persistent tcgen05 kernel, csrc/attn_fused.cuh), "split"
+    (compaction pass + mma.sync dense pass) or "single" (one mma.sync kernel).  Shapes the fused kernel does not
+    handle (more than 8 agents per scene) run the single kernel.  workspace: caller-owned scratch (uint8, at least
+    attn_workspace_bytes); records_valid=True reuses the key records an earlier fused call left in it (same geometry
+    and kind) instead of recomputing them."""
     args = _lib.AttnArgs()
-    if split is None:
-        split = L <= 8 and os.environ.get("HMVIT_ATTN_SPLIT", "1") != "0"
-    if split:
-        ws = _attn_workspace(B, L, H, W, q.device)
+    args.impl = _IMPL[impl]
+    if args.impl != _lib.ATTN_SINGLE:
+        ws = workspace if workspace is not None else _attn_workspace(args.impl, B, L, H, W, q.device)
         args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+        args.records_valid = 1 if (records_valid and workspace is not None) else 0
     args.B, args.L, args.H, args.W = B, L, H, W
     args.kind = kind
     args.ego_only = 1 if ego_only else 0
@@ -212,17 +218,15 @@ def roi_cav_mask(T: torch.Tensor, cav_mask: torch.Tensor, H: int, W: int, cell: 
     return out
 
 
-def fusion_workspace_bytes(B, L, H, W) -> int:
-    return int(_lib.load().hmvit_fusion_workspace_bytes(B, L, H, W))
+def attn_workspace_bytes(B, L, H, W, impl=None) -> int:
+    return int(_lib.load().hmvit_group_attn_workspace_bytes(_IMPL[impl], B, L, H, W))
 
 
-def fusion_launch_count(num_iters, head, skip_dead=True) -> int:
+def fusion_workspace_bytes(B, L, H, W, unfused=False, attn_impl=None) -> int:
+    return int(_lib.load().hmvit_fusion_workspace_bytes(B, L, H, W, 1 if unfused else 0, _IMPL[attn_impl]))
+
+
+def fusion_launch_count(num_iters, head, skip_dead=True, attn_impl=None) -> int:
     """Kernel launches of one hmvit_fusion_forward.  With skip_dead (the module default) the head runs inside the last
     stage's chain launch instead of a launch of its own."""
-    return int(_lib.load().hmvit_fusion_launch_count(num_iters, (2 if skip_dead else 1) if head else 0))
-
-
-def debug_probe(device="cuda"):
-    out = torch.zeros(2, dtype=torch.int32, device=device)
-    _lib.check(_lib.load().hmvit_debug_probe(out.data_ptr(), _stream()))
-    return [int(v) & 0xFFFFFFFF for v in out.cpu().tolist()]
+    return int(_lib.load().hmvit_fusion_launch_count(num_iters, (2 if skip_dead else 1) if head else 0, _IMPL[attn_impl]))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMVIT_ABI_VERSION 4
+#define HMVIT_ABI_VERSION 5
 
 /* error codes */
 #define HMVIT_OK 0
@@ -135,11 +135,26 @@ int hmvit_ffn_head(const HmvitHeadArgs* args, void* stream);
  * Replaces HeteroFusionBlock.warp_features + the ego loop around HeteroAttention.forward
  *   opencood/models/sub_modules/hetero_fusion.py:338-361, 373-397 (window) / 412-440 (grid), 187-277
  * and the warp / ROI-mask helpers it calls
- *   opencood/models/sub_modules/torch_transformation_utils.py:11-134, 254-355. */
+ *   opencood/models/sub_modules/torch_transformation_utils.py:11-134, 254-355.
+ * Three implementations of the same contract, selected explicitly (no environment switches):
+ *   HMVIT_ATTN_FUSED   default: a key-record pass (fp64 source-pixel maps, bit-exact ROI visibility, compaction of the
+ *                      visible keys; csrc/attn_fused.cuh tap_records_kernel) + ONE persistent warp-specialised tcgen05
+ *                      kernel whose gather warps blend the projected K' / V' taps straight into shared-memory operand
+ *                      tiles (fused_attn_kernel).  Needs a workspace for the records; handles L <= 8 agents per scene
+ *                      and B*L <= 1024 (larger shapes run HMVIT_ATTN_SINGLE).
+ *   HMVIT_ATTN_SPLIT   round-1 form, kept as an independently written cross-check: warp + compaction pass writing dense
+ *                      key / value tiles to the workspace, then an mma.sync dense attention pass (csrc/attn_split.cuh).
+ *   HMVIT_ATTN_SINGLE  one mma.sync kernel per (ego, group, head group), gather inside (csrc/attn.cuh); no workspace,
+ *                      any L. */
+enum { HMVIT_ATTN_FUSED = 0, HMVIT_ATTN_SPLIT = 1, HMVIT_ATTN_SINGLE = 2 };
+
 typedef struct {
   int32_t B, L, H, W;
   int32_t kind;               /* 0 = window partition, 1 = grid partition */
   int32_t ego_only;           /* only ego slot 0 of each scene */
+  int32_t impl;               /* HMVIT_ATTN_* */
+  int32_t records_valid;      /* HMVIT_ATTN_FUSED: 1 = `workspace` already holds this call's key records (same geometry
+                                 arguments and kind; written by an earlier call) -- the record pass is skipped */
   const int32_t* mode;
   const int32_t* record_len;
   const int32_t* cav_mask;
@@ -156,15 +171,13 @@ typedef struct {
   void* out;                  /* bf16 rows [B*L*N][256] */
   float* lse;                 /* optional [B*L*N][8]: log2-domain log-sum-exp per (query token, head), saved for
                                  hmvit_group_attn_bwd; NULL = not written (inference) */
-  void* workspace;            /* optional scratch of >= hmvit_group_attn_workspace_bytes(B, L, H, W) bytes (256-byte
-                                 aligned).  Non-NULL selects the split form: a warp + compaction pass writes the
-                                 visible, blended keys / values of every (ego, group) as dense 64-key tiles, then a
-                                 dense attention pass consumes them (csrc/attn_split.cuh).  NULL: single kernel. */
+  void* workspace;            /* scratch of >= hmvit_group_attn_workspace_bytes(impl, B, L, H, W) bytes, 256-byte aligned
+                                 (FUSED: key records; SPLIT: compacted tiles; SINGLE: unused, may be NULL) */
   size_t workspace_bytes;
 } HmvitAttnArgs;
 
 int hmvit_group_attn(const HmvitAttnArgs* args, void* stream);
-size_t hmvit_group_attn_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W);
+size_t hmvit_group_attn_workspace_bytes(int32_t impl, int32_t B, int32_t L, int32_t H, int32_t W);
 
 /* ---- stand-alone spatial warp and ROI mask (unit-parity surface) ------------------------------------
  * SpatialTransformation.forward  opencood/models/sub_modules/spatial_transformation.py:16-44
@@ -216,17 +229,20 @@ typedef struct {
   const void* head_w2[2];
   const float* head_b2;
   float* xres;                /* fp32 cm [B*L][256][N]: residual stream / block output (valid slots) */
-  void* workspace;            /* hmvit_fusion_workspace_bytes() bytes */
+  void* workspace;            /* hmvit_fusion_workspace_bytes(B, L, H, W, unfused, attn_impl) bytes, 256-byte aligned */
   float* out;                 /* fp32 [B][256][N] (head == 1) */
   const void* head_w1h[2];    /* fp16 [256][256] copies of head_w1 / head_w2 for the fused head kernel */
   const void* head_w2h[2];
+  int32_t attn_impl;          /* HMVIT_ATTN_*: 0 = the fused persistent tcgen05 attention (default); the others are
+                                 cross-check forms (shapes the fused kernel does not handle run HMVIT_ATTN_SINGLE) */
 } HmvitFusionArgs;
 
-size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W);
+size_t hmvit_fusion_workspace_bytes(int32_t B, int32_t L, int32_t H, int32_t W, int32_t unfused, int32_t attn_impl);
 int hmvit_fusion_forward(const HmvitFusionArgs* args, void* stream);
-/* number of kernel launches one hmvit_fusion_forward enqueues (for launch accounting); head: 0 = no head, 1 = head as
- * its own launch (skip_dead == 0 or unfused), 2 = head with skip_dead (runs inside the last stage's chain launch) */
-int hmvit_fusion_launch_count(int32_t num_iters, int32_t head);
+/* number of kernel launches one hmvit_fusion_forward enqueues (for launch accounting): the key-record pass + per stage
+ * {QKV, attention, chain}; head: 0 = no head, 1 = head as its own launch (skip_dead == 0), 2 = head with skip_dead (runs
+ * inside the last stage's chain launch) */
+int hmvit_fusion_launch_count(int32_t num_iters, int32_t head, int32_t attn_impl);
 
 /* ---- backward pass (training configuration) ---------------------------------------------------------
  * The reference differentiates the fusion module with autograd (train_camera.py:172-193).  Here the
@@ -285,10 +301,6 @@ typedef struct {
   float* dbk; float* dbv; float* dbias_table;
 } HmvitAttnBwdArgs;
 int hmvit_group_attn_bwd(const HmvitAttnBwdArgs* args, void* stream);
-
-/* ---- bring-up / self-test helpers ---------------------------------------------------------------------
- * Writes {dynamic-smem base address & 1023, TMEM base of the first allocation} for diagnostics. */
-int hmvit_debug_probe(uint32_t* out2, void* stream);
 
 #ifdef __cplusplus
 }

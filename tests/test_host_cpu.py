@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(pkg._lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert pkg._lib.load().hmvit_abi_version() == 4
+    assert pkg._lib.load().hmvit_abi_version() == pkg._lib.ABI_VERSION == 5
 
 
 def test_state_dict_keys_match_reference_spec():
@@ -104,14 +104,17 @@ def test_emulation_restructuring_is_exact():
 
 
 def test_launch_accounting():
-    """hmvit_fusion_launch_count is pure host code: per stage QKV + compaction + dense attention + chain; the head is a
-    launch of its own only without dead-query elimination (with it, it runs inside the last stage's chain launch)."""
+    """hmvit_fusion_launch_count is pure host code: one key-record pass per forward + per stage QKV + attention + chain;
+    the head is a launch of its own only without dead-query elimination (with it, it runs inside the last stage's chain
+    launch).  The split cross-check form has two attention launches per stage and no record pass."""
     pkg = hmvit_loader.load()
     ops = pkg.ops
-    assert ops.fusion_launch_count(2, False) == 16
-    assert ops.fusion_launch_count(2, True, skip_dead=False) == 17
-    assert ops.fusion_launch_count(2, True, skip_dead=True) == 16
-    assert ops.fusion_launch_count(1, True) == 8
+    assert ops.fusion_launch_count(2, False) == 13
+    assert ops.fusion_launch_count(2, True, skip_dead=False) == 14
+    assert ops.fusion_launch_count(2, True, skip_dead=True) == 13
+    assert ops.fusion_launch_count(1, True) == 7
+    assert ops.fusion_launch_count(2, True, attn_impl="split") == 16
+    assert ops.fusion_launch_count(2, True, attn_impl="single") == 12
 
 
 
