@@ -752,6 +752,10 @@ extern "C" int hmvit_group_attn_bwd(const HmvitAttnBwdArgs* a, void* stream) {
 // ------------------------------------------------------------------------------------------------
 // timeline instrumentation (tools/build_variant.sh -DHMVIT_TS builds only; not part of the product library)
 // ------------------------------------------------------------------------------------------------
+extern "C" int hmvit_debug_fa_ts(unsigned long long* host_out /* [2][4][1024] */) {
+  HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_fa_ts, sizeof(unsigned long long) * 2 * 4 * 1024));
+  return HMVIT_OK;
+}
 extern "C" int hmvit_debug_qkv_ts(unsigned long long* host_out /* [3][512] */) {
   HMVIT_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_qkv_ts, sizeof(unsigned long long) * 3 * 512));
   return HMVIT_OK;

@@ -114,6 +114,28 @@ HMVIT_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// non-blocking phase test
+HMVIT_DEVINL bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// wait of a role that is idle for a long time (an item's duration): sleeps between polls so that its spin loop does not
+// take issue slots from the working warps
+HMVIT_DEVINL void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (++spins > (1u << 24)) { asm volatile("trap;"); }
+  }
+}
+
 // one lane of a CONVERGED warp (elect.sync): the warp keeps executing uniformly around a single-thread instruction,
 // so the compiler can hold descriptors / addresses in uniform registers (an `if (lane == 0)` region makes every
 // operand of a tcgen05.mma go through a per-instruction R2UR loop: ~100 issue cycles per MMA, measured)
@@ -270,6 +292,11 @@ HMVIT_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+HMVIT_DEVINL void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 HMVIT_DEVINL void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

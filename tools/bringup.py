@@ -38,7 +38,7 @@ if __name__ == "__main__":
         for n in names:
             try:
                 r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", n], capture_output=True,
-                                   text=True, timeout=300, cwd=ROOT)
+                                   text=True, timeout=int(os.environ.get('BRINGUP_TIMEOUT', '300')), cwd=ROOT)
                 lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
                 line = lines[-1] if lines else json.dumps({"check": n, "status": "CRASH", "rc": r.returncode,
                                                            "stderr": r.stderr[-600:]})

@@ -1,7 +1,8 @@
-"""Time the attention forms at the bench shape (config 2): single fused kernel vs the split form
-(warp + compaction pass, dense attention pass), per partition; also reports their output difference.
-HMVIT_LIB=<variant .so> selects the build."""
-import ctypes, json, os, sys
+"""Time the attention implementations at the bench shape (config 2), per partition kind and for the ego-only stage:
+fused persistent tcgen05 kernel (with valid key records), the key-record pass alone, the split form and the single
+kernel; also reports the output difference fused vs single.  HMVIT_LIB=<variant .so> selects a tuning build
+(tools/build_variant.sh); TIME_ATTN_IMPLS=fused[,split,single] restricts the forms."""
+import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
@@ -25,8 +26,7 @@ rows = B * L * N
 qkv = torch.empty(5, rows, C, dtype=torch.bfloat16, device=dev)
 cell = float(blk.discrete_ratio) * float(blk.downsample_rate)
 common = dict(B=B, L=L, N=N, mode=mode, record_len=rl)
-so = lib.load()
-so.hmvit_debug_split_phase.argtypes = [ctypes.c_int]
+impls = os.environ.get("TIME_ATTN_IMPLS", "fused,split,single").split(",")
 
 
 def t_ms(fn, iters=10):
@@ -41,9 +41,10 @@ def t_ms(fn, iters=10):
 
 res = {"lib": os.environ.get("HMVIT_LIB", "default")}
 with torch.no_grad():
-    for _ in range(30):                                   # clocks up before anything is timed
+    for _ in range(20):                                   # clocks up before anything is timed
         net(x, T, mode, rl, cav)
     torch.cuda.synchronize()
+    ws = torch.empty(max(ops.attn_workspace_bytes(B, L, H, W), 256), dtype=torch.uint8, device=dev)
     for kind, kname in ((0, "window"), (1, "grid")):
         w = pk[kname]
         ops.rowgemm(lib.GEMM_QKV, n_out=1280, a=x, w0=w["wqkv0"], w1=w["wqkv1"], bias=w["bqkv"], out=qkv, **common)
@@ -52,20 +53,20 @@ with torch.no_grad():
                 continue
             outs = {}
 
-            def run(split, tag):
+            def run(impl, tag, **kw):
                 out = outs.setdefault(tag, torch.zeros(rows, C, dtype=torch.bfloat16, device=dev))
                 ops.group_attn(B=B, L=L, H=H, W=W, kind=kind, mode=mode, record_len=rl, cav_mask=cav, T=T, cell=cell,
                                q=qkv[0], k=qkv[1:3], v=qkv[3:5], bk=w["bk"], bv=w["bv"], bias_table=w["bias_table"],
-                               out=out, ego_only=dead, split=split)
+                               out=out, ego_only=dead, impl=impl, **kw)
             name = kname + ("_ego" if dead else "")
-            res[name + "_single"] = round(t_ms(lambda: run(False, "single")), 4)
-            res[name + "_split"] = round(t_ms(lambda: run(True, "split")), 4)
-            so.hmvit_debug_split_phase(1)
-            res[name + "_compact"] = round(t_ms(lambda: run(True, "tmp")), 4)
-            so.hmvit_debug_split_phase(2)
-            res[name + "_dense"] = round(t_ms(lambda: run(True, "tmp")), 4)
-            so.hmvit_debug_split_phase(0)
-            d = (outs["single"].float() - outs["split"].float())
-            res[name + "_maxdiff"] = float(d.abs().max())
-            res[name + "_rel_l2"] = float(d.norm() / outs["single"].float().norm())
+            if "fused" in impls:
+                run("fused", "fused", workspace=ws, records_valid=False)
+                res[name + "_fused"] = round(t_ms(lambda: run("fused", "fused", workspace=ws, records_valid=True)), 4)
+                res[name + "_fused+records"] = round(t_ms(lambda: run("fused", "fused", workspace=ws, records_valid=False)), 4)
+            for impl in ("split", "single"):
+                if impl in impls:
+                    res[name + "_" + impl] = round(t_ms(lambda: run(impl, impl)), 4)
+            if "fused" in impls and "single" in impls:
+                d = (outs["single"].float() - outs["fused"].float())
+                res[name + "_fused_vs_single_rel_l2"] = float(d.norm() / outs["single"].float().norm())
 print(json.dumps(res))
