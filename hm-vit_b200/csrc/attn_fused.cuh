@@ -155,16 +155,13 @@ struct FaCfg {
   static constexpr int OFF_KVB = OFF_BIAS + kHG * kBiasStride * 4;     // [2 te][2 tj][K | V][128 ch] bf16 folded biases
   static constexpr int OFF_KOFF = OFF_KVB + 2 * 2 * 2 * 256;           // [4 tiles][64] byte offset of every key's bias column
   static constexpr int OFF_VALID = OFF_KOFF + 4 * 64 * 4;              // [kFusedMaxAgents] uint16: agents that own work items
-  static constexpr int OFF_BAR = OFF_VALID + kFusedMaxAgents * 2;
+  static constexpr int OFF_NV = OFF_VALID + kFusedMaxAgents * 2;       // [NV_ITEMS] uint16: visible keys of this CTA's k-th item
+  static constexpr int NV_ITEMS = 2048;
+  static constexpr int OFF_BAR = OFF_NV + NV_ITEMS * 2;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;              // + alignment slack
   static constexpr uint32_t TM_COLS = 256;              // pair p: S / P at 128 p, D at 128 p + 64
 };
 
-HMVIT_DEVINL int ldg_nc_s32_volatile(const int* p) {      // issued where written: a prefetch the compiler may not sink
-  int v;
-  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
 // 16-byte read-only global load, issued in program order; pred == false: no load, zeros
 HMVIT_DEVINL uint4 ldg_nc_u4_if(const uint4* p, bool pred) {
   uint4 v;
@@ -202,6 +199,7 @@ __global__ void __launch_bounds__(FaCfg::THREADS, 2) fused_attn_kernel(const Fus
   uint8_t* sKvb = smem + Cfg::OFF_KVB;
   int* sKoff = reinterpret_cast<int*>(smem + Cfg::OFF_KOFF);
   uint16_t* sValid = reinterpret_cast<uint16_t*>(smem + Cfg::OFF_VALID);
+  uint16_t* sNv = reinterpret_cast<uint16_t*>(smem + Cfg::OFF_NV);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* kv_full = bars + 0;      // [2 stages]  gather warps -> MMA
   uint64_t* kv_empty = bars + 2;     // [2 stages]  MMA (commit) -> gather warps
@@ -268,6 +266,19 @@ __global__ void __launch_bounds__(FaCfg::THREADS, 2) fused_attn_kernel(const Fus
   // this CTA's items: (valid agent, group) pairs, strided over the CTAs that share its head group
   const int n_items = nvalid * G;
   const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+  // Visible-key counts of this CTA's items, staged in shared memory once: a per-item global load sat on every role's
+  // critical path at each item boundary (a register prefetch does not survive: ptxas spills it right behind the load,
+  // which waits for it -- 18 % of the softmax warps' stall samples).  Items beyond the table fall back to global loads.
+  for (int k = tid; k < Cfg::NV_ITEMS; k += Cfg::THREADS) {
+    const int it_ = item0 + k * item_step;
+    if (it_ >= n_items) break;
+    sNv[k] = static_cast<uint16_t>(__ldg(fp.nvis + static_cast<size_t>(sValid[it_ / G]) * G + (it_ - (it_ / G) * G)));
+  }
+  __syncthreads();
+  auto item_nv = [&](int k_, int it_) -> int {                    // visible keys of this CTA's k-th item (= item it_)
+    if (k_ < Cfg::NV_ITEMS) return sNv[k_];
+    return __ldg(fp.nvis + static_cast<size_t>(sValid[it_ / G]) * G + (it_ - (it_ / G) * G));
+  };
 
   if (warp < 4) {
     // =========================================== SOFTMAX ===========================================
@@ -278,17 +289,11 @@ __global__ void __launch_bounds__(FaCfg::THREADS, 2) fused_attn_kernel(const Fus
     const int bias_q = ((row >> 3) + 7) * 15 + (row & 7) + 7;
     uint32_t tcnt = 0, icnt = 0;
     int ts_i = 0; (void)ts_i;
-    auto item_nv = [&](int it_) -> int {                          // visible keys of item it_ (0 past the end)
-      if (it_ >= n_items) return 0;
-      const int a_ = sValid[it_ / G];
-      return ldg_nc_s32_volatile(fp.nvis + static_cast<size_t>(a_) * G + (it_ - (it_ / G) * G));
-    };
-    int nv_next = item_nv(item0);
-    for (int it = item0; it < n_items; it += item_step) {
+    int kit = 0;
+    for (int it = item0; it < n_items; it += item_step, ++kit) {
       const int a = sValid[it / G], grp = it - (it / G) * G;
       const int gy = grp / GX, gx = grp - gy * GX;
-      const int nv = nv_next;
-      nv_next = item_nv(it + item_step);                          // requested one item ahead
+      const int nv = item_nv(kit, it);
       const int ntiles = (nv + kS - 1) >> 6;
       int r, c; group_token(p.kind, gy, gx, row, p.H, p.W, r, c);
       const size_t tok = static_cast<size_t>(a) * N + r * p.W + c;
@@ -459,24 +464,22 @@ __global__ void __launch_bounds__(FaCfg::THREADS, 2) fused_attn_kernel(const Fus
       }
     };
     uint4 rec_next = make_uint4(0, 0, 0, 0);
-    int nv_next = 0;
     uint32_t icnt = 0;
     if (item0 < n_items) {
       int a_, g_; item_of(item0, a_, g_);
-      nv_next = __ldg(fp.nvis + static_cast<size_t>(a_) * G + g_);
       rec_next = __ldg(rec_ptr(a_, g_) + mykey);
       prefetch_q(a_, g_);
     }
-    for (int it = item0; it < n_items; it += item_step) {
+    int kit = 0;
+    for (int it = item0; it < n_items; it += item_step, ++kit) {
       int a, grp; item_of(it, a, grp);
       const int b = a / p.L;
-      const int nv = nv_next;
+      const int nv = item_nv(kit, it);
       const int ntiles = (nv + kS - 1) >> 6;
       const int it_n = it + item_step;
       int a_n = a, grp_n = grp;
       if (it_n < n_items) {
         item_of(it_n, a_n, grp_n);
-        nv_next = __ldg(fp.nvis + static_cast<size_t>(a_n) * G + grp_n);
         prefetch_q(a_n, grp_n);
       }
       if (ntiles == 0 && it_n < n_items) rec_next = __ldg(rec_ptr(a_n, grp_n) + mykey);
@@ -603,15 +606,9 @@ __global__ void __launch_bounds__(FaCfg::THREADS, 2) fused_attn_kernel(const Fus
     };
     uint32_t tcnt = 0, icnt = 0;
     int ts_i = 0; (void)ts_i;
-    auto item_nv = [&](int it_) -> int {
-      if (it_ >= n_items) return 0;
-      const int a_ = sValid[it_ / G];
-      return ldg_nc_s32_volatile(fp.nvis + static_cast<size_t>(a_) * G + (it_ - (it_ / G) * G));
-    };
-    int nv_next = item_nv(item0);
-    for (int it = item0; it < n_items; it += item_step) {
-      const int nv = nv_next;
-      nv_next = item_nv(it + item_step);
+    int kit = 0;
+    for (int it = item0; it < n_items; it += item_step, ++kit) {
+      const int nv = item_nv(kit, it);
       const int ntiles = (nv + kS - 1) >> 6;
       if (ntiles == 0) continue;
       if (lane == 0) FA_TS(2, ts_i++, 1);                           // item start (waiting for tile 0)

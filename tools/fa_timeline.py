@@ -45,3 +45,14 @@ for cta in range(1):
         lo = int(os.environ.get("TS_FROM", "120"))
         print(names[r], len(ev), f"events; (code:delta-to-previous) from event {lo}:")
         print(" ".join(f"{c}:{t - ev[i - 1][1]}" for i, (c, t) in enumerate(ev) if lo <= i < lo + 170))
+# merged absolute timeline of CTA 0 (TS_ABS=1): time, role, code
+if os.environ.get("TS_ABS"):
+    allev = []
+    for r in range(4):
+        allev += [((int(v) >> 8) - t0, names[r], int(v) & 0xff) for v in buf[0, r] if v]
+    allev.sort()
+    lo, hi = int(os.environ.get("TS_T0", "300000")), int(os.environ.get("TS_T1", "380000"))
+    print("merged timeline (cycles since first event):")
+    for t, n, c in allev:
+        if lo <= t < hi:
+            print(f"{t:8d} {n:8s} {c}")
