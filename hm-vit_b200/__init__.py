@@ -10,7 +10,6 @@ from .fusion import (HeteroAttention, HeteroFeedForward, HeteroFusion, HeteroFus
 from .build import build_extension  # noqa: F401
 from .sharding import max_over_ranks, scene_shard  # noqa: F401
 from .distributed import FlatGradAllReduce  # noqa: F401
-from .distributed import FlatGradAllReduce  # noqa: F401
 
 __all__ = ["HeteroFusion", "HeteroFusionBlock", "HeteroAttention", "HeteroLayerNorm", "HeteroFeedForward",
            "HeteroPreNormResidual", "SpatialTransformation", "get_roi_and_cav_mask", "regroup",

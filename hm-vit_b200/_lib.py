@@ -19,7 +19,7 @@ EXPORTS = (
     "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
     "hmvit_out_ffn_chain", "hmvit_ffn_head",
     "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
-    "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes",
+    "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes", "hmvit_dropout",
 )
 
 
@@ -135,6 +135,8 @@ def load():
     lib.hmvit_bwd_cast_bf16.argtypes = [vp, vp, C.c_size_t, vp]
     lib.hmvit_bwd_colsum.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp]
     lib.hmvit_bwd_wgrad.argtypes = [C.POINTER(WgradArgs), vp]
+    lib.hmvit_dropout.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, C.c_uint64, C.c_uint32, C.c_float, vp]
+    lib.hmvit_dropout.restype = C.c_int
     lib.hmvit_group_attn_bwd.argtypes = [C.POINTER(AttnBwdArgs), vp]
     for fn in ("hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
                "hmvit_bwd_wgrad", "hmvit_group_attn_bwd"):

@@ -7,6 +7,7 @@
 #include "attn_fused.cuh"
 #include "attn_bwd.cuh"
 #include "bwd.cuh"
+#include "dropout.cuh"
 #include "chain.cuh"
 #include "qkv.cuh"
 
@@ -692,6 +693,23 @@ extern "C" int hmvit_bwd_colsum(const void* y, int32_t rows_bf16, float* db, int
     dim3 grid(256 / 8, B * L);
     colsum_cm_kernel<<<grid, 256, 0, st>>>(static_cast<const float*>(y), db, db_stride, L, N, mode, record_len, ego_only ? 1 : 0);
   }
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+extern "C" int hmvit_dropout(const float* a, const float* resid, float* out, int32_t B, int32_t L, int32_t N,
+                             const int32_t* record_len, int32_t ego_only, uint64_t seed, uint32_t stream_id, float p, void* stream) {
+  HMVIT_CHECK_ARG(out && record_len, "dropout: null pointer");
+  HMVIT_CHECK_ARG(B > 0 && L > 0 && N > 0 && B * L <= 65535 && N % 4 == 0, "dropout: bad shape (N must be a multiple of 4)");
+  HMVIT_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p must be in [0, 1)");
+  DropoutParams q;
+  q.a = a; q.resid = resid; q.out = out; q.L = L; q.N = N; q.record_len = record_len; q.ego_only = ego_only ? 1 : 0;
+  q.seed_lo = static_cast<uint32_t>(seed); q.seed_hi = static_cast<uint32_t>(seed >> 32); q.stream = stream_id;
+  const double th = static_cast<double>(p) * 4294967296.0;
+  q.threshold = th >= 4294967295.0 ? 4294967295u : static_cast<uint32_t>(th);
+  q.scale = 1.0f / (1.0f - p);
+  dim3 grid((N / 4 + 255) / 256, 256, B * L);
+  dropout_cm_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(q);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }

@@ -94,7 +94,7 @@ HMVIT_DEVINL void group_token(int kind, int gy, int gx, int s, int H, int W, int
 __global__ void __launch_bounds__(kAttnThreads, 4) group_attn_kernel(const AttnParams p) {
   const int a = blockIdx.y;
   const int b = a / p.L, i = a - b * p.L;
-  const int nrec = p.record_len[b];
+  const int nrec = min(p.record_len[b], p.L);            // a malformed record_len must not index past the scene's slots
   if (i >= nrec || (p.ego_only && i != 0)) return;
   const int N = p.H * p.W;
   const int GX = p.W / kWin;

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
   using Cfg = AttnBwdCfg;
   const int a = blockIdx.y;
   const int b = a / p.L, i = a - b * p.L;
-  const int nrec = p.record_len[b];
+  const int nrec = min(p.record_len[b], p.L);            // a malformed record_len must not index past the scene's slots
   if (i >= nrec || (p.ego_only && i != 0)) return;
   const int N = p.H * p.W;
   const int GX = p.W / kWin;

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kCompactThreads, 4) warp_compact_kernel(const 
   const AttnParams& p = sp.a;
   const int a = blockIdx.y;
   const int b = a / p.L, i = a - b * p.L;
-  const int nrec = p.record_len[b];
+  const int nrec = min(p.record_len[b], p.L);            // a malformed record_len must not index past the scene's slots
   if (i >= nrec || (p.ego_only && i != 0)) return;
   const int N = p.H * p.W;
   const int GX = p.W / kWin, G = (p.H / kWin) * GX;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kDenseThreads, HMVIT_DENSE_CTAS) dense_attn_ke
   const AttnParams& p = sp.a;
   const int a = blockIdx.y;
   const int b = a / p.L, i = a - b * p.L;
-  const int nrec = p.record_len[b];
+  const int nrec = min(p.record_len[b], p.L);            // a malformed record_len must not index past the scene's slots
   if (i >= nrec || (p.ego_only && i != 0)) return;
   const int N = p.H * p.W;
   const int GX = p.W / kWin, G = (p.H / kWin) * GX;

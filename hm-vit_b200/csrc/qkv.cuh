@@ -128,7 +128,7 @@ qkv_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CU
     a = t / tiles_per_agent;
     tok0 = (t - a * tiles_per_agent) * Cfg::BM;
     const int b = a / p.L, l = a - b * p.L;
-    const int nrec = p.record_len[b];
+    const int nrec = min(p.record_len[b], p.L);
     if (l >= nrec) return false;
     uint32_t te_mask = 0;
     if (p.ego_only) te_mask = 1u << (p.mode[b * p.L] != 0 ? 1 : 0);

@@ -72,7 +72,7 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
   using Cfg = RowGemmCfg<ES>;
   const int a = blockIdx.y;
   const int b = a / p.L, l = a - b * p.L;
-  const int nrec = p.record_len[b];
+  const int nrec = min(p.record_len[b], p.L);
   if (l >= nrec || (p.tile_ego_only && l != 0)) return;
   const int type = p.mode[a] != 0 ? 1 : 0;
   const int tok0 = blockIdx.x * Cfg::BM;

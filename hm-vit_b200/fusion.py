@@ -153,6 +153,10 @@ class HeteroAttention(nn.Module):
         """Folded projection weights.  With ln_gamma / ln_beta ([2][C], per type) the affine of the
         preceding typed LayerNorm is folded in as well:  W (g*z + b) + c = (W diag g) z + (W b + c)."""
         Cd, h, d = self._dim, self.heads, self._dim_head
+        # the fused attention kernel bounds its probabilities by 2^(8 + max|bias| log2 e): keep that inside fp32 range
+        bmax = float(self.relative_position_bias_table.weight.detach().abs().max())
+        if not bmax <= 40.0:
+            raise ValueError(f"relative_position_bias_table: |bias| up to {bmax:.1f} exceeds the supported range of +-40")
         att, msg = self.relation_att.detach().float(), self.relation_msg.detach().float()
         wqkv, bqkv = [], []
         bk = torch.empty(2, 2, Cd, device=att.device)
@@ -244,24 +248,37 @@ def _wants_grad(module: nn.Module, x: torch.Tensor) -> bool:
     return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters()))
 
 
-def _check_dropout(block):
-    # the reference applies Dropout(p) after a_linears and twice in the FFN in train mode (hetero_fusion.py:66,
-    # base_transformer.py:186-190); bit-parity with its RNG is impossible, and the kernels have no dropout yet
-    if block.training and block.drop_out > 0:
-        raise NotImplementedError(
-            f"hmvit_b200 training path: drop_out={block.drop_out} in train mode is not supported -- set drop_out: 0 "
-            "in the yaml or call .eval() (gradients are still computed)")
+def _dropout_args(block):
+    """(p, seed) of this forward.  The reference applies Dropout(p) after a_linears and twice in the FFN in train mode
+    (hetero_fusion.py:66, base_transformer.py:186-190); here the three sites draw from a counter-based Philox stream
+    (csrc/dropout.cuh) keyed by a per-forward seed: `block.dropout_seed` when set (reproducible runs / mask export in the
+    tests), else a fresh draw from torch's default generator (so torch.manual_seed governs it).  Same distribution as
+    the reference, not the same bits as torch's own RNG."""
+    if not (block.training and block.drop_out > 0):
+        return 0.0, 0
+    seed = block.dropout_seed
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    block.last_dropout_seed = seed
+    return float(block.drop_out), seed
 
 
-def _check_inputs(block, x):
+def _check_inputs(block, x, pairwise_t_matrix, mode, record_len, mask):
+    """Shape / device validation shared by the inference and the training entry of the module.  (record_len values are
+    clamped to L inside the kernels, so a malformed value cannot index past a scene's slots without a host sync here.)"""
     if x.dim() != 5:
         raise ValueError(f"x: expected (B, L, C, H, W), got {tuple(x.shape)}")
     if not x.is_cuda:
         raise ValueError("hmvit_b200 runs on CUDA tensors only (no CPU fallback)")
-    if x.shape[2] != 256:
-        raise ValueError(f"x: channel dim must be 256, got {x.shape[2]}")
-    if x.shape[3] % block.window_size or x.shape[4] % block.window_size:
-        raise ValueError(f"H={x.shape[3]}, W={x.shape[4]} must be divisible by the window size {block.window_size}")
+    B, L, Cc, H, W = x.shape
+    if Cc != 256:
+        raise ValueError(f"x: channel dim must be 256, got {Cc}")
+    if H % block.window_size or W % block.window_size:
+        raise ValueError(f"H={H}, W={W} must be divisible by the window size {block.window_size}")
+    if tuple(pairwise_t_matrix.shape) != (B, L, L, 4, 4):
+        raise ValueError(f"pairwise_t_matrix: expected {(B, L, L, 4, 4)}, got {tuple(pairwise_t_matrix.shape)}")
+    if tuple(mode.shape) != (B, L) or tuple(mask.shape) != (B, L) or tuple(record_len.shape) != (B,):
+        raise ValueError("mode / mask must be (B, L) and record_len (B,)")
 
 
 class HeteroFusionBlock(nn.Module):
@@ -270,6 +287,8 @@ class HeteroFusionBlock(nn.Module):
 
     attn_impl = None      # attention implementation inside hmvit_fusion_forward (see HeteroAttention.attn_impl)
     unfused_chain = False  # True: OUT / FFN1 / FFN2 as three row-GEMMs instead of the fused chain kernel (cross-check)
+    dropout_seed = None    # int: fixed Philox seed of the train-mode Dropout (None: drawn per forward)
+    last_dropout_seed = None
 
     def __init__(self, config):
         super().__init__()
@@ -320,10 +339,28 @@ class HeteroFusionBlock(nn.Module):
         return pk
 
     def packed(self):
+        """Folded / cast weights, cached on (data_ptr, version) of every parameter.  In-place writes through `.data`
+        (EMA swaps, `p.data.copy_`) do not bump the version: call invalidate_packed() after them.  load_state_dict,
+        `.to()` / `.half()` (`_apply`) and `.train()` drop the cache themselves."""
         key = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._pack_cache is None or self._pack_cache[0] != key:
             self._pack_cache = (key, {"window": self._stage_pack("window"), "grid": self._stage_pack("grid")})
         return self._pack_cache[1]
+
+    def invalidate_packed(self):
+        self._pack_cache = None
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._pack_cache = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._pack_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode=True):
+        self._pack_cache = None
+        return super().train(mode)
 
     def forward(self, x, pairwise_t_matrix, mode, record_len, mask):
         """x (B, L, C, H, W) -> (B, L, C, H, W).  Valid slots (l < record_len[b]) hold the block output;
@@ -331,9 +368,10 @@ class HeteroFusionBlock(nn.Module):
         if self.architect_mode != 'sequential':
             raise ValueError(f"{self.architect_mode} not implemented")
         if _wants_grad(self, x):
-            _check_inputs(self, x)
-            _check_dropout(self)
-            return training.fusion_train(ops, self, None, x, pairwise_t_matrix, mode, record_len, mask, num_iters=1)
+            _check_inputs(self, x, pairwise_t_matrix, mode, record_len, mask)
+            p, seed = _dropout_args(self)
+            return training.fusion_train(ops, self, None, x, pairwise_t_matrix, mode, record_len, mask, num_iters=1,
+                                         drop_p=p, seed=seed)
         xres = x.detach().float().clone().contiguous()
         _run_fusion(self, None, x, pairwise_t_matrix, mode, record_len, mask, num_iters=1, xres=xres)
         return xres
@@ -369,15 +407,32 @@ class HeteroFusion(nn.Module):
             self._head_cache = (key, pk)
         return self._head_cache[1]
 
+    def invalidate_packed(self):
+        """Drop the packed-weight caches of the head and of the block (after in-place writes through `.data`)."""
+        self._head_cache = None
+        self.hetero_fusion_block.invalidate_packed()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._head_cache = None
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._head_cache = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode=True):
+        self._head_cache = None
+        return super().train(mode)
+
     def forward(self, x, pairwise_t_matrix, mode, record_len, mask):
         blk = self.hetero_fusion_block
         if blk.architect_mode != 'sequential':
             raise ValueError(f"{blk.architect_mode} not implemented")
         if _wants_grad(self, x):
-            _check_inputs(blk, x)
-            _check_dropout(blk)
+            _check_inputs(blk, x, pairwise_t_matrix, mode, record_len, mask)
+            p, seed = _dropout_args(blk)
             return training.fusion_train(ops, blk, self, x, pairwise_t_matrix, mode, record_len, mask,
-                                         num_iters=self.num_iters, skip_dead=self.skip_dead_queries)
+                                         num_iters=self.num_iters, skip_dead=self.skip_dead_queries, drop_p=p, seed=seed)
         return _run_fusion(blk, self, x, pairwise_t_matrix, mode, record_len, mask, num_iters=self.num_iters)
 
 
@@ -411,25 +466,14 @@ def _fill_stage(sw: "_lib.StageWeights", pk: Dict[str, torch.Tensor]):
 
 
 def _run_fusion(block: HeteroFusionBlock, fusion, x, pairwise_t_matrix, mode, record_len, mask, num_iters, xres=None):
-    if x.dim() != 5:
-        raise ValueError(f"x: expected (B, L, C, H, W), got {tuple(x.shape)}")
-    if not x.is_cuda:
-        raise ValueError("hmvit_b200 runs on CUDA tensors only (no CPU fallback)")
+    _check_inputs(block, x, pairwise_t_matrix, mode, record_len, mask)
     B, L, Cc, H, W = x.shape
-    if Cc != 256:
-        raise ValueError(f"x: channel dim must be 256, got {Cc}")
-    if H % block.window_size or W % block.window_size:
-        raise ValueError(f"H={H}, W={W} must be divisible by the window size {block.window_size}")
     dev = x.device
     x = x.detach().float().contiguous()
     T = pairwise_t_matrix.detach().to(device=dev, dtype=torch.float32).contiguous()
-    if T.shape != (B, L, L, 4, 4):
-        raise ValueError(f"pairwise_t_matrix: expected {(B, L, L, 4, 4)}, got {tuple(T.shape)}")
     mode_i = mode.detach().to(device=dev, dtype=torch.int32).contiguous()
     rl = record_len.detach().to(device=dev, dtype=torch.int32).contiguous()
     cav = mask.detach().to(device=dev, dtype=torch.int32).contiguous()
-    if mode_i.shape != (B, L) or cav.shape != (B, L) or rl.shape != (B,):
-        raise ValueError("mode / mask must be (B, L) and record_len (B,)")
 
     head = fusion is not None
     if xres is None:

@@ -198,6 +198,15 @@ def group_attn_bwd(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, 
     _lib.check(_lib.load().hmvit_group_attn_bwd(C.byref(args), _stream()))
 
 
+def dropout(a, out, *, B, L, N, record_len, seed, stream_id, p, resid=None, ego_only=False):
+    """out = resid + keep * a / (1 - p) on cm fp32 (B*L, 256, N) tensors; a=None exports the scaled mask.  The mask is a
+    pure function of (seed, stream_id, element index): the backward regenerates it with the same arguments."""
+    _lib.check(_lib.load().hmvit_dropout(a.data_ptr() if a is not None else None, resid.data_ptr() if resid is not None else None,
+                                         out.data_ptr(), B, L, N, record_len.data_ptr(), 1 if ego_only else 0,
+                                         int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id) & 0xFFFFFFFF, float(p), _stream()))
+    return out
+
+
 def warp_bilinear(x: torch.Tensor, T: torch.Tensor, cell: float) -> torch.Tensor:
     """x (n, C, H, W) fp32, T (n, 4, 4) fp32 source->target.  Returns the warped maps (n, C, H, W)."""
     _chk(x, torch.float32, "x"), _chk(T, torch.float32, "T")

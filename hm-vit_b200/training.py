@@ -149,8 +149,16 @@ class _Saved:
     pass
 
 
-def forward_train(ops, geo, x, packs, head_pack, num_iters, skip_dead):
-    """Stage-by-stage forward through the per-kernel entry points.  Returns (out | None, last x, saved)."""
+def _drop_stream(stage: int, site: int) -> int:
+    """Philox stream of a Dropout site: site 0 = behind a_linears (hetero_fusion.py:66), 1 = behind the FFN's GELU,
+    2 = behind the FFN's second Linear (base_transformer.py:186-190)."""
+    return stage * 4 + site
+
+
+def forward_train(ops, geo, x, packs, head_pack, num_iters, skip_dead, drop_p=0.0, seed=0):
+    """Stage-by-stage forward through the per-kernel entry points.  Returns (out | None, last x, saved).
+    drop_p > 0 (train mode of the shipped yaml): the three Dropout sites of a stage sit between the GEMMs, so the stage
+    runs as row-GEMMs + the Philox dropout kernel instead of the fused chain kernel; masks are regenerated, not saved."""
     B, L, H, W = geo["B"], geo["L"], geo["H"], geo["W"]
     N = H * W
     R = B * L * N
@@ -176,9 +184,26 @@ def forward_train(ops, geo, x, packs, head_pack, num_iters, skip_dead):
                        q=qkv[0], k=qkv[1:3], v=qkv[3:5], bk=pk["bk"], bv=pk["bv"], bias_table=pk["bias_table"],
                        out=att, ego_only=dead, lse=lse)
         xout = torch.zeros_like(xin)
-        ops.out_ffn_chain(o=att, resid=xin, out=xout, wa0=pk["wa0"], wa1=pk["wa1"], ba=pk["ba"],
-                          w1_0=pk["w1h_0"], w1_1=pk["w1h_1"], b1=pk["b1"], w2_0=pk["w2h_0"], w2_1=pk["w2h_1"], b2=pk["b2"],
-                          ego_only=dead, **common)
+        if drop_p > 0.0:
+            dk = dict(B=B, L=L, N=N, record_len=rl, seed=seed, p=drop_p, ego_only=dead)
+            tmp = torch.zeros_like(xin)
+            xp = torch.zeros_like(xin)
+            ops.rowgemm(_lib.GEMM_ROWS_LIN_CM, n_out=C_DIM, a=att, w0=pk["wa0"], w1=pk["wa1"], bias=pk["ba"], out=tmp,
+                        ego_only=dead, **common)
+            ops.dropout(tmp, xp, resid=xin, stream_id=_drop_stream(s, 0), **dk)          # x' = x + Dropout(O Wa^T + ba)
+            ops.rowgemm(_lib.GEMM_FFN1, n_out=C_DIM, a=xp, w0=pk["w1_0"], w1=pk["w1_1"], bias=pk["b1"], out=tmp,
+                        ego_only=dead, **common)                                        # gelu(W1' LN(x') + b1')
+            ops.dropout(tmp, tmp, stream_id=_drop_stream(s, 1), **dk)
+            hid = tmp
+            tmp = torch.zeros_like(xin)
+            ops.rowgemm(_lib.GEMM_LIN_CM, n_out=C_DIM, a=hid, w0=pk["w2_0"], w1=pk["w2_1"], bias=pk["b2"], out=tmp,
+                        ego_only=dead, **common)
+            ops.dropout(tmp, xout, resid=xp, stream_id=_drop_stream(s, 2), **dk)         # x'' = x' + Dropout(W2 h + b2)
+            del tmp, hid, xp
+        else:
+            ops.out_ffn_chain(o=att, resid=xin, out=xout, wa0=pk["wa0"], wa1=pk["wa1"], ba=pk["ba"],
+                              w1_0=pk["w1h_0"], w1_1=pk["w1h_1"], b1=pk["b1"], w2_0=pk["w2h_0"], w2_1=pk["w2h_1"], b2=pk["b2"],
+                              ego_only=dead, **common)
         sv.qkv.append(qkv); sv.att.append(att); sv.lse.append(lse); sv.dead.append(dead); sv.xs.append(xout)
     out = None
     if head:
@@ -201,9 +226,11 @@ def _zero_grads(dev) -> Dict[str, torch.Tensor]:
             "w2": z(2, C_DIM, C_DIM), "b2": z(2, C_DIM), "bias_table": z(225, 8)}
 
 
-def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xlast: Optional[torch.Tensor]):
+def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xlast: Optional[torch.Tensor],
+             drop_p=0.0, seed=0):
     """Returns (dx [B*L, 256, N] fp32, [grads window, grads grid], head grads | None): gradients of the folded
-    weights.  d_out: gradient of the head output (B, 256, N); d_xlast: gradient of the block output (no head)."""
+    weights.  d_out: gradient of the head output (B, 256, N); d_xlast: gradient of the block output (no head).
+    drop_p / seed: the forward's Dropout arguments (the masks are regenerated from them)."""
     B, L, H, W = geo["B"], geo["L"], geo["H"], geo["W"]
     N = H * W
     R = B * L * N
@@ -216,6 +243,7 @@ def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xl
     zero_b = torch.zeros(2, C_DIM, dtype=torch.float32, device=dev)
     grads = [_zero_grads(dev), _zero_grads(dev)]
     hp, dh, dz, xp = f32(), f32(), f32(), f32()
+    dmk = f32() if drop_p > 0.0 else None                           # masked copy of a gradient (Dropout adjoint)
     st = torch.zeros(R, 2, dtype=torch.float32, device=dev)
 
     def lin_cm(a, w0, w1, bias, out, ego):
@@ -251,25 +279,42 @@ def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xl
         pk, g = packs[kind], grads[kind]
         dead = sv.dead[s]
         xin, qkv, att, lse = sv.xs[s], sv.qkv[s], sv.att[s], sv.lse[s]
-        # ---- recompute x' = x + O Wa^T + ba and the FFN pre-activation ----
-        ops.rowgemm(_lib.GEMM_ROWS_LIN_CM, n_out=C_DIM, a=att, w0=pk["wa0"], w1=pk["wa1"], bias=pk["ba"], resid=xin, out=xp,
-                    ego_only=dead, **common)
+        dk = dict(B=B, L=L, N=N, record_len=rl, seed=seed, p=drop_p, ego_only=dead)
+        # ---- recompute x' = x + [Dropout](O Wa^T + ba) and the FFN pre-activation ----
+        if drop_p > 0.0:
+            ops.rowgemm(_lib.GEMM_ROWS_LIN_CM, n_out=C_DIM, a=att, w0=pk["wa0"], w1=pk["wa1"], bias=pk["ba"], out=dmk,
+                        ego_only=dead, **common)
+            ops.dropout(dmk, xp, resid=xin, stream_id=_drop_stream(s, 0), **dk)
+        else:
+            ops.rowgemm(_lib.GEMM_ROWS_LIN_CM, n_out=C_DIM, a=att, w0=pk["wa0"], w1=pk["wa1"], bias=pk["ba"], resid=xin, out=xp,
+                        ego_only=dead, **common)
         ops.bwd_row_stats(xp, st, ego_only=dead, **geo3)
         ops.rowgemm(_lib.GEMM_LN_LIN_CM, n_out=C_DIM, a=xp, w0=pk["w1_0"], w1=pk["w1_1"], bias=pk["b1"], out=hp,
                     ego_only=dead, **common)
-        # ---- FFN: x'' = x' + W2 gelu(W1' LN(x') + b1') + b2 ----
-        lin_cm(dX, pk["w2T0"], pk["w2T1"], zero_b, dh, dead)
+        # ---- FFN: x'' = x' + [Dropout](W2 [Dropout](gelu(W1' LN(x') + b1')) + b2) ----
+        dff = dX                                                     # gradient of the FFN output
+        if drop_p > 0.0:
+            ops.dropout(dX, dmk, stream_id=_drop_stream(s, 2), **dk)
+            dff = dmk
+        lin_cm(dff, pk["w2T0"], pk["w2T1"], zero_b, dh, dead)
         ops.bwd_gelu(hp, dh)                                         # hp <- gelu(hp), dh <- d pre-activation
-        ops.bwd_wgrad(dX, hp, g["w2"], ego_only=dead, **common)
-        ops.bwd_colsum(dX, g["b2"], ego_only=dead, **common)
+        if drop_p > 0.0:                                             # the hidden Dropout commutes with the GELU derivative
+            ops.dropout(hp, hp, stream_id=_drop_stream(s, 1), **dk)
+            ops.dropout(dh, dh, stream_id=_drop_stream(s, 1), **dk)
+        ops.bwd_wgrad(dff, hp, g["w2"], ego_only=dead, **common)
+        ops.bwd_colsum(dff, g["b2"], ego_only=dead, **common)
         ops.bwd_wgrad(dh, xp, g["w1"], b_stats=st, ego_only=dead, **common)
         ops.bwd_colsum(dh, g["b1"], ego_only=dead, **common)
         lin_cm(dh, pk["w1T0"], pk["w1T1"], zero_b, dz, dead)
         ops.bwd_layernorm(dz, xp, st, dX, dX, ego_only=dead, **geo3)   # dX: gradient w.r.t. x'
         # ---- output projection ----
-        ops.bwd_wgrad(dX, att, g["wa"], ego_only=dead, **common)
-        ops.bwd_colsum(dX, g["ba"], ego_only=dead, **common)
-        ops.rowgemm(_lib.GEMM_LIN_ROWS, n_out=C_DIM, a=dX, w0=pk["waT0"], w1=pk["waT1"], bias=zero_b, out=dO,
+        dpr = dX                                                     # gradient of O Wa^T + ba
+        if drop_p > 0.0:
+            ops.dropout(dX, dmk, stream_id=_drop_stream(s, 0), **dk)
+            dpr = dmk
+        ops.bwd_wgrad(dpr, att, g["wa"], ego_only=dead, **common)
+        ops.bwd_colsum(dpr, g["ba"], ego_only=dead, **common)
+        ops.rowgemm(_lib.GEMM_LIN_ROWS, n_out=C_DIM, a=dpr, w0=pk["waT0"], w1=pk["waT1"], bias=zero_b, out=dO,
                     ego_only=dead, **common)
         # ---- attention (+ warp scatter) ----
         dqkv.zero_()
@@ -294,14 +339,15 @@ def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xl
 # ----------------------------------------------------------------------------------------------
 class _FusionFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, ops, block, fusion, geo, num_iters, skip_dead, *params):
+    def forward(ctx, x, ops, block, fusion, geo, num_iters, skip_dead, drop_p, seed, *params):
         rows_dtype = getattr(ops, "ROWS_DTYPE", torch.bfloat16)
         with torch.no_grad():
             packs = [kernel_pack_stage(fold_stage(block, k), rows_dtype) for k in ("window", "grid")]
             head_pack = kernel_pack_head(fold_head(fusion), rows_dtype) if fusion is not None else None
             xin = x.detach().float().reshape(geo["B"] * geo["L"], C_DIM, geo["H"] * geo["W"]).contiguous()
-            out, xlast, sv = forward_train(ops, geo, xin, packs, head_pack, num_iters, skip_dead)
+            out, xlast, sv = forward_train(ops, geo, xin, packs, head_pack, num_iters, skip_dead, drop_p, seed)
         ctx.ops, ctx.block, ctx.fusion, ctx.geo = ops, block, fusion, geo
+        ctx.drop_p, ctx.seed = drop_p, seed
         ctx.sv, ctx.packs, ctx.head_pack = sv, packs, head_pack
         ctx.n_params = len(params)
         ctx.x_shape = x.shape
@@ -318,9 +364,9 @@ class _FusionFn(torch.autograd.Function):
         with torch.no_grad():
             d_y = d_y.detach().float().contiguous()
             if fusion is not None:
-                dX, grads, head_grads = backward(ctx.ops, geo, ctx.sv, ctx.packs, ctx.head_pack, d_y, None)
+                dX, grads, head_grads = backward(ctx.ops, geo, ctx.sv, ctx.packs, ctx.head_pack, d_y, None, ctx.drop_p, ctx.seed)
             else:
-                dX, grads, head_grads = backward(ctx.ops, geo, ctx.sv, ctx.packs, None, None, d_y)
+                dX, grads, head_grads = backward(ctx.ops, geo, ctx.sv, ctx.packs, None, None, d_y, ctx.drop_p, ctx.seed)
         ctx.sv = None                                                  # free the saved activations
         # padded slots: the kernels never touch them, so they keep 0 (head path) or the incoming gradient (block
         # path, where padded slots pass through the forward unchanged)
@@ -344,12 +390,17 @@ class _FusionFn(torch.autograd.Function):
             pg = torch.autograd.grad(outs, req, gouts, allow_unused=True) if (req and outs) else tuple(None for _ in req)
         it = iter(pg)
         gparams = [next(it) if p.requires_grad else None for p in params]
-        return (dx if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, *gparams)
+        return (dx if ctx.needs_input_grad[0] else None, None, None, None, None, None, None, None, None, *gparams)
 
 
-def fusion_train(ops, block, fusion, x, pairwise_t_matrix, mode, record_len, mask, num_iters, skip_dead=True):
-    """Differentiable fusion forward (x and the module parameters).  fusion = None: block only."""
+def fusion_train(ops, block, fusion, x, pairwise_t_matrix, mode, record_len, mask, num_iters, skip_dead=True,
+                 drop_p=0.0, seed=0):
+    """Differentiable fusion forward (x and the module parameters).  fusion = None: block only.  drop_p > 0: train-mode
+    Dropout (p of the yaml) with the Philox stream `seed`."""
     B, L, Cc, H, W = x.shape
+    if tuple(pairwise_t_matrix.shape) != (B, L, L, 4, 4) or tuple(mode.shape) != (B, L) or tuple(mask.shape) != (B, L) \
+            or tuple(record_len.shape) != (B,):
+        raise ValueError("pairwise_t_matrix must be (B, L, L, 4, 4), mode / mask (B, L) and record_len (B,)")
     dev = x.device
     geo = {"B": B, "L": L, "H": H, "W": W,
            "T": pairwise_t_matrix.detach().to(device=dev, dtype=torch.float32).contiguous(),
@@ -359,4 +410,4 @@ def fusion_train(ops, block, fusion, x, pairwise_t_matrix, mode, record_len, mas
            "cell": float(block.discrete_ratio) * float(block.downsample_rate)}
     owner = fusion if fusion is not None else block
     params = list(owner.parameters())
-    return _FusionFn.apply(x, ops, block, fusion, geo, num_iters, skip_dead, *params)
+    return _FusionFn.apply(x, ops, block, fusion, geo, num_iters, skip_dead, float(drop_p), int(seed), *params)

@@ -266,6 +266,15 @@ int hmvit_bwd_cast_bf16(const float* src, void* dst, size_t n, void* stream);
 int hmvit_bwd_colsum(const void* y, int32_t rows_bf16, float* db, int32_t db_stride, int32_t B, int32_t L, int32_t N,
                      const int32_t* mode, const int32_t* record_len, int32_t ego_only, void* stream);
 
+/* Dropout of the training path (the shipped yaml trains with drop_out: 0.1):
+ *   nn.Dropout after a_linears    opencood/models/sub_modules/hetero_fusion.py:66
+ *   nn.Dropout x 2 in the FFN     opencood/models/base_transformer.py:186-190
+ * out = resid + keep(seed, stream_id, i) * a / (1 - p) over cm fp32 tensors [B*L][256][N] (N % 4 == 0); resid may be NULL;
+ * a == NULL exports the scaled mask itself (tests hand it to the CPU oracle).  keep() is Philox4x32-10 keyed by `seed`
+ * with counter (element index / 4, stream_id): never stored, the backward regenerates it with the same arguments. */
+int hmvit_dropout(const float* a, const float* resid, float* out, int32_t B, int32_t L, int32_t N, const int32_t* record_len,
+                  int32_t ego_only, uint64_t seed, uint32_t stream_id, float p, void* stream);
+
 /* typed weight gradient  dW[type][row0 + m][n] += sum_tok A(tok, m) B(tok, n)  (m, n < 256), tf32 tensor cores */
 typedef struct {
   int32_t B, L, N;

@@ -188,14 +188,19 @@ def hetero_layer_norm(x: Tensor, mode: Tensor, P: Dict[str, Tensor], pfx: str, e
     return out
 
 
-def hetero_ffn(x: Tensor, mode: Tensor, P: Dict[str, Tensor], pfx: str) -> Tensor:
-    """Linear -> GELU(erf) -> Linear per type (dropout is identity in eval)."""
+def hetero_ffn(x: Tensor, mode: Tensor, P: Dict[str, Tensor], pfx: str, drop=None) -> Tensor:
+    """Linear -> GELU(erf) -> Dropout -> Linear -> Dropout per type (base_transformer.py:180-192).  Dropout is the
+    identity in eval; training parity passes the scaled keep masks drop = {"hid": ..., "ffn": ...} (same shape as x)."""
     out = None
     for t in (0, 1):
         sel = mode == t
         if sel.any():
             h = F.gelu(F.linear(x[sel], P[f"{pfx}.net.{t}.0.weight"], P[f"{pfx}.net.{t}.0.bias"]))
+            if drop is not None:
+                h = h * drop["hid"][sel]
             y = F.linear(h, P[f"{pfx}.net.{t}.3.weight"], P[f"{pfx}.net.{t}.3.bias"])
+            if drop is not None:
+                y = y * drop["ffn"][sel]
             if out is None:
                 out = x.new_empty(*x.shape[:-1], y.shape[-1])
             out[sel] = y
@@ -239,8 +244,10 @@ def hetero_attention_ego(xw: Tensor, types: Tensor, ego: int, keymask: Tensor, P
 # one stage (window or grid) of the fusion block (hetero_fusion.py:363-444)
 # --------------------------------------------------------------------------
 def fusion_stage(x: Tensor, T: Tensor, mode: Tensor, record_len: Tensor, cav_mask: Tensor,
-                 P: Dict[str, Tensor], pfx: str, kind: str, cfg: dict) -> Tensor:
-    """x (B, L, H, W, C) channels-last residual stream -> same shape."""
+                 P: Dict[str, Tensor], pfx: str, kind: str, cfg: dict, drop=None) -> Tensor:
+    """x (B, L, H, W, C) channels-last residual stream -> same shape.  drop: optional scaled keep masks of the three
+    train-mode Dropout sites of the stage, {"att", "hid", "ffn"}, each (B, L, H, W, C) (hetero_fusion.py:66,
+    base_transformer.py:186-190); None = eval."""
     B, L, H, W, C = x.shape
     w = cfg["window_size"]
     dr, ds = cfg["spatial_transform"]["voxel_size"][0], cfg["spatial_transform"]["downsample_rate"]
@@ -262,33 +269,38 @@ def fusion_stage(x: Tensor, T: Tensor, mode: Tensor, record_len: Tensor, cav_mas
             y = hetero_attention_ego(xw, mode[b, :Lv], i, km, P, f"{pfx}.{kind}_attention",
                                      cfg["dim_head"], w)
             upd[b, i].view(H * W, C)[table.reshape(-1)] = y.reshape(G * S, C)
+    if drop is not None:
+        upd = upd * drop["att"]                                              # Dropout behind a_linears (:66)
     x = x + upd                                                              # :399
     xn2 = hetero_layer_norm(x, mode, P, f"{pfx}.{kind}_ffd.norm")
-    return x + hetero_ffn(xn2, mode, P, f"{pfx}.{kind}_ffd.fn")              # :401
+    return x + hetero_ffn(xn2, mode, P, f"{pfx}.{kind}_ffd.fn", drop)        # :401
 
 
 def fusion_block(x: Tensor, T: Tensor, mode: Tensor, record_len: Tensor, cav_mask: Tensor,
-                 P: Dict[str, Tensor], cfg: dict, pfx: str = "hetero_fusion_block") -> Tensor:
+                 P: Dict[str, Tensor], cfg: dict, pfx: str = "hetero_fusion_block", drop_masks=None) -> Tensor:
     """HeteroFusionBlock.forward, architect_mode == 'sequential' (hetero_fusion.py:446-458).
     x (B, L, C, H, W) -> (B, L, C, H, W)."""
     if cfg.get("architect_mode", "sequential") != "sequential":
         raise ValueError(f"{cfg.get('architect_mode')} not implemented")
     y = x.permute(0, 1, 3, 4, 2).contiguous()
-    y = fusion_stage(y, T, mode, record_len, cav_mask, P, pfx, "window", cfg)
-    y = fusion_stage(y, T, mode, record_len, cav_mask, P, pfx, "grid", cfg)
+    y = fusion_stage(y, T, mode, record_len, cav_mask, P, pfx, "window", cfg, drop_masks[0] if drop_masks is not None else None)
+    y = fusion_stage(y, T, mode, record_len, cav_mask, P, pfx, "grid", cfg, drop_masks[1] if drop_masks is not None else None)
     return y.permute(0, 1, 4, 2, 3).contiguous()
 
 
 def hetero_fusion(x: Tensor, T: Tensor, mode: Tensor, record_len: Tensor, cav_mask: Tensor,
-                  P: Dict[str, Tensor], config: dict) -> Tensor:
+                  P: Dict[str, Tensor], config: dict, drop_masks=None) -> Tensor:
     """HeteroFusion.forward (bevformer_point_pillar_hetero.py:39-49): num_iters x the same block,
-    ego slice, typed FFN head (no norm, no residual).  Returns (B, C, H, W)."""
+    ego slice, typed FFN head (no norm, no residual; its Dropout has p = 0).  Returns (B, C, H, W).
+    drop_masks: optional list (one entry per stage, 2 * num_iters) of train-mode Dropout masks, see fusion_stage."""
     mode = mode.to(torch.int64)
     cfg = config["hetero_fusion_block"]
     y = x.permute(0, 1, 3, 4, 2).contiguous()
-    for _ in range(config["num_iters"]):
-        y = fusion_stage(y, T, mode, record_len, cav_mask, P, "hetero_fusion_block", "window", cfg)
-        y = fusion_stage(y, T, mode, record_len, cav_mask, P, "hetero_fusion_block", "grid", cfg)
+    for it in range(config["num_iters"]):
+        dw = drop_masks[2 * it] if drop_masks is not None else None
+        dg = drop_masks[2 * it + 1] if drop_masks is not None else None
+        y = fusion_stage(y, T, mode, record_len, cav_mask, P, "hetero_fusion_block", "window", cfg, dw)
+        y = fusion_stage(y, T, mode, record_len, cav_mask, P, "hetero_fusion_block", "grid", cfg, dg)
     ego = y[:, :1]                                                           # (B, 1, H, W, C)
     out = hetero_ffn(ego, mode[:, :1], P, "mlp_head")
     return out[:, 0].permute(0, 3, 1, 2).contiguous()

@@ -64,12 +64,12 @@ def rowgemm(variant, *, B, L, N, n_out, mode, record_len, a, w0, w1, bias, out, 
             A = a[ai * N:(ai + 1) * N].float()
         else:
             A = a[ai].t().float()
-            if variant == GEMM_LN_LIN_CM:
+            if variant in (GEMM_LN_LIN_CM, GEMM_FFN1):
                 A = _ln(A, ln_eps)
         y = A @ w[t].t() + bias[t]
-        if resid is not None and variant in (GEMM_OUT, GEMM_ROWS_LIN_CM):
+        if resid is not None and variant in (GEMM_OUT, GEMM_ROWS_LIN_CM, GEMM_FFN2):
             y = y + resid[ai].t()
-        if variant == GEMM_HEAD1:
+        if variant in (GEMM_HEAD1, GEMM_FFN1):
             y = F.gelu(y)
         if variant == GEMM_LIN_ROWS:
             out[ai * N:(ai + 1) * N] = y.to(out.dtype)
@@ -221,3 +221,42 @@ def bwd_wgrad(a, b, dw, *, B, L, N, mode, record_len, ego_only=False, b_stats=No
             Bm = (Bm - st[:, :1]) * st[:, 1:]
         dw[t, row0:row0 + C] += _operand(a, ai, N).t() @ Bm
     return dw
+
+
+# ---- dropout: the same counter-based mask as csrc/dropout.cuh (Philox4x32-10), in numpy --------------------
+def _philox4x32_10(c0, c1, c2, c3, k0, k1):
+    import numpy as np
+    M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    c = [c0.astype(np.uint64), c1.astype(np.uint64), c2.astype(np.uint64), c3.astype(np.uint64)]
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    mask32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask32, p1 >> np.uint64(32), p1 & mask32
+        c = [(hi1 ^ c[1] ^ k0) & mask32, lo1, (hi0 ^ c[3] ^ k1) & mask32, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & mask32
+        k1 = (k1 + np.uint64(0xBB67AE85)) & mask32
+    return c
+
+
+def dropout_mask_cm(agents, N, seed, stream_id, p):
+    """Scaled keep mask (agents, 256, N) fp32 = what hmvit_dropout(a=NULL) writes for active agents."""
+    import numpy as np
+    assert N % 4 == 0
+    nblk = agents * C * N // 4
+    idx = np.arange(nblk, dtype=np.uint64)
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    r = _philox4x32_10(idx & np.uint64(0xFFFFFFFF), idx >> np.uint64(32), np.full(nblk, int(stream_id) & 0xFFFFFFFF, dtype=np.uint64),
+                       np.zeros(nblk, dtype=np.uint64), seed & 0xFFFFFFFF, seed >> 32)
+    r = np.stack(r, axis=1).reshape(-1)                        # 4 consecutive elements per block
+    th = min(int(float(np.float32(p)) * 4294967296.0), 4294967295)
+    keep = (r >= np.uint64(th)).astype(np.float32) * np.float32(1.0 / (1.0 - float(np.float32(p))))
+    return torch.from_numpy(keep.reshape(agents, C, N))
+
+
+def dropout(a, out, *, B, L, N, record_len, seed, stream_id, p, resid=None, ego_only=False):
+    m = dropout_mask_cm(B * L, N, seed, stream_id, p).to(out.device)
+    for b, l, ai in _agents(B, L, record_len, ego_only):
+        v = m[ai] if a is None else a[ai] * m[ai]
+        out[ai] = v + (resid[ai] if resid is not None else 0.0)
+    return out

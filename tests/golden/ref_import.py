@@ -10,7 +10,20 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("HMVIT_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _find_root() -> str:
+    """the reference installed under baseline/_ref/ (pip --target, git-ignored, travels to the GPU
+    box), then /root/reference (build container only); HMVIT_REFERENCE overrides."""
+    cands = [os.environ.get("HMVIT_REFERENCE"), os.path.join(_REPO, "baseline", "_ref"), "/root/reference"]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "opencood")):
+            return c
+    return cands[-1]
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

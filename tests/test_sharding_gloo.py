@@ -77,6 +77,15 @@ def _train_worker(rank, world, port, out):
     bucket = pkg.FlatGradAllReduce(net)
     bucket.allreduce(dist)
     after = {n: (None if p.grad is None else p.grad.clone()) for n, p in net.named_parameters()}
+    # second step: the gradients are views of the bucket now (no pack / unpack): zero, backward, reduce again
+    attached = all(p.grad is None or p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    bucket.zero_grad()
+    y = pkg.training.fusion_train(emul_ops, net.hetero_fusion_block, net, x, T, m, rl, mask, num_iters=net.num_iters)
+    y.square().mean().backward()
+    still = all(p.grad is None or p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+    bucket.allreduce(dist)
+    step2_bad = [n for n, p in net.named_parameters()
+                 if (after[n] is None) != (p.grad is None) or (p.grad is not None and not torch.allclose(p.grad, after[n], rtol=1e-5, atol=1e-8))]
     gathered = [None] * world
     dist.all_gather_object(gathered, local)
     if rank == 0:
@@ -92,7 +101,7 @@ def _train_worker(rank, world, port, out):
             ref = sum(q for q in parts if q is not None) / world
             if g is None or not torch.allclose(g, ref, rtol=1e-6, atol=1e-8):
                 bad.append(name)
-        out.put((n_none, bad, bucket.nbytes, len(after)))
+        out.put((n_none, bad + step2_bad, bucket.nbytes, len(after), attached and still))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -104,10 +113,11 @@ def test_data_parallel_gradient_allreduce_world2_gloo():
     procs = [ctx.Process(target=_train_worker, args=(r, world, 29741, out)) for r in range(world)]
     for p in procs:
         p.start()
-    n_none, bad, nbytes, n_params = out.get(timeout=300)
+    n_none, bad, nbytes, n_params, views_ok = out.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert 10_000_000 < nbytes < 10_100_000                    # 2.5 M fp32 parameters + flags in ONE bucket
+    assert 10_000_000 < nbytes < 10_100_000                    # 2.5 M fp32 parameters in ONE bucket
+    assert views_ok                                            # .grad of every used parameter is a view into the bucket
     assert not bad, bad                                        # every gradient == mean over ranks
     assert n_none == 8 and n_params > 80                       # aggregate_fc (unused on every rank) stays None

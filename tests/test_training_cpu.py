@@ -160,3 +160,88 @@ def test_gradients_match_reference_autograd_golden():
                                   skip_dead=True)
     (y * g_out).sum().backward()
     compare(xg.grad, {n: p.grad for n, p in net.named_parameters()}, 2e-4, 5e-4)
+
+
+def _oracle_drop_masks(B, L, H, W, n_stage, seed, p):
+    """The train-mode Dropout masks of the product path (Philox streams of hmvit_b200/training.py), exported in the
+    oracle's (B, L, H, W, C) layout: list over stages of {"att", "hid", "ffn"}."""
+    N = H * W
+    pkg = hmvit_loader.load()
+    out = []
+    for s in range(n_stage):
+        d = {}
+        for site, name in enumerate(("att", "hid", "ffn")):
+            m = emul_ops.dropout_mask_cm(B * L, N, seed, pkg.training._drop_stream(s, site), p)      # (B*L, 256, N)
+            d[name] = m.view(B, L, 256, H, W).permute(0, 1, 3, 4, 2).contiguous()
+        out.append(d)
+    return out
+
+
+def test_dropout_training_matches_oracle_with_replayed_masks():
+    """Train mode with the shipped yaml's drop_out = 0.1: the product orchestration (forward with the three Dropout sites per
+    stage + backward that regenerates the masks) against torch.autograd through the oracle with the SAME masks replayed
+    (hetero_fusion.py:66, base_transformer.py:186-190 sites)."""
+    pkg, cfg, P, net, inp = _setup(2, 3, 16, 24, [3, 2], seed=13)
+    x, T, m, rl, mask = inp
+    p_drop, seed = 0.1, 123456789
+    g_out = torch.randn(2, 256, 16, 24, generator=torch.Generator().manual_seed(5))
+    masks = _oracle_drop_masks(2, 3, 16, 24, 2 * cfg["num_iters"], seed, p_drop)
+    Pg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in P.items()}
+    xr = x.clone().requires_grad_(True)
+    y_ref = O.hetero_fusion(xr, T, m, rl, mask, Pg, cfg, drop_masks=masks)
+    names = [k for k, v in Pg.items() if v.is_floating_point()]
+    gs = torch.autograd.grad((y_ref * g_out).sum(), [xr] + [Pg[k] for k in names], allow_unused=True)
+    g_ref = dict(zip(["x"] + names, gs))
+    y_eval = O.hetero_fusion(x, T, m, rl, mask, P, cfg)
+    assert _rel(y_ref.detach(), y_eval) > 0.05                      # the masks really change the result
+
+    xg = x.clone().requires_grad_(True)
+    y = pkg.training.fusion_train(emul_ops, net.hetero_fusion_block, net, xg, T, m, rl, mask, num_iters=net.num_iters,
+                                  skip_dead=True, drop_p=p_drop, seed=seed)
+    assert _rel(y.detach(), y_ref.detach()) < 1e-4
+    (y * g_out).sum().backward()
+    assert _rel(xg.grad, g_ref["x"]) < 5e-4
+    worst = 0.0
+    for name, prm in net.named_parameters():
+        ref = g_ref.get(name)
+        if ref is None or "aggregate_fc" in name:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
+            continue
+        if float(ref.norm()) < 1e-6:
+            continue
+        worst = max(worst, _rel(prm.grad, ref))
+    assert worst < 2e-3, worst
+
+
+def test_dropout_mask_statistics_and_streams():
+    """Keep rate of the Philox mask within 4 sigma of 1 - p, values in {0, 1/(1-p)}, independent streams."""
+    p = 0.1
+    a = emul_ops.dropout_mask_cm(2, 1024, 77, 0, p)
+    b = emul_ops.dropout_mask_cm(2, 1024, 77, 1, p)
+    c = emul_ops.dropout_mask_cm(2, 1024, 78, 0, p)
+    n = a.numel()
+    scale = 1.0 / (1.0 - float(torch.tensor(p, dtype=torch.float32)))
+    vals = sorted(torch.unique(a).tolist())
+    assert len(vals) == 2 and vals[0] == 0.0 and vals[1] == pytest.approx(scale)
+    for m in (a, b, c):
+        keep = float((m != 0).float().mean())
+        assert abs(keep - (1 - p)) < 4 * (p * (1 - p) / n) ** 0.5
+    for u, v in ((a, b), (a, c)):
+        agree = float(((u != 0) == (v != 0)).float().mean())
+        assert abs(agree - ((1 - p) ** 2 + p ** 2)) < 0.01              # independent masks agree with prob. 0.82
+    assert torch.equal(a, emul_ops.dropout_mask_cm(2, 1024, 77, 0, p))  # pure function of (seed, stream, index)
+
+
+def test_module_train_mode_dispatch_cpu():
+    """The module surface in train mode no longer rejects drop_out > 0: it draws a Philox seed per forward (or uses
+    block.dropout_seed); CPU tensors still raise (no fallback)."""
+    pkg, cfg, P, net, inp = _setup(1, 2, 8, 8, [2], seed=1)
+    blk = net.hetero_fusion_block
+    blk.drop_out = 0.1
+    net.train()
+    p, seed = pkg.fusion._dropout_args(blk)
+    assert p == pytest.approx(0.1) and blk.last_dropout_seed == seed
+    blk.dropout_seed = 42
+    assert pkg.fusion._dropout_args(blk) == (pytest.approx(0.1), 42)
+    net.eval()
+    assert pkg.fusion._dropout_args(blk) == (0.0, 0)

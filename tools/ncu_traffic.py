@@ -1,5 +1,5 @@
 """Extract per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of every profiled kernel from an
-ncu --set full report and write profiles/r1_traffic.json (read by bench.py for roofline.traffic).
+ncu --set full report and write profiles/r2_traffic.json (read by bench.py for roofline.traffic).
 Usage (build container): python tools/ncu_traffic.py gpurun_out/s5_prof.ncu-rep"""
 import csv
 import json
@@ -29,7 +29,7 @@ def main():
                "profiled_duration_" + units[it]: v["dur"] / v["launches"]} for k, v in acc.items()}
     res["_source"] = {"report": os.path.basename(rep),
                       "command": sys.argv[2] if len(sys.argv) > 2 else "ncu --set full --clock-control none --import-source on ... python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-train"}
-    json.dump(res, open(os.path.join(ROOT, "profiles", "r1_traffic.json"), "w"), indent=1)
+    json.dump(res, open(os.path.join(ROOT, "profiles", "r2_traffic.json"), "w"), indent=1)
     print(json.dumps(res, indent=1))
 
 
