@@ -19,7 +19,7 @@ EXPORTS = (
     "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
     "hmvit_out_ffn_chain", "hmvit_ffn_head",
     "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
-    "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes", "hmvit_dropout",
+    "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes", "hmvit_dropout", "hmvit_attn_records",
 )
 
 
@@ -114,6 +114,8 @@ def load():
     lib.hmvit_ffn_head.restype = C.c_int
     lib.hmvit_group_attn.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
     lib.hmvit_group_attn.restype = C.c_int
+    lib.hmvit_attn_records.argtypes = [C.POINTER(AttnArgs), C.c_void_p]
+    lib.hmvit_attn_records.restype = C.c_int
     lib.hmvit_group_attn_workspace_bytes.argtypes = [C.c_int32] * 5
     lib.hmvit_group_attn_workspace_bytes.restype = C.c_size_t
     lib.hmvit_warp_bilinear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,

@@ -343,6 +343,15 @@ static int launch_fused_attn(const AttnParams& p, const KeyRec* rec, const int* 
   return HMVIT_OK;
 }
 
+extern "C" int hmvit_attn_records(const HmvitAttnArgs* a, void* stream) {
+  AttnParams p;
+  int rc = fill_attn_params(a, p); if (rc) return rc;
+  HMVIT_CHECK_ARG(fused_applicable(a->B, a->L), "attn_records: at most 8 agents per scene and B*L <= 1024");
+  HMVIT_CHECK_ARG(a->workspace != nullptr && a->workspace_bytes >= records_bytes(a->B, a->L, a->H, a->W), "attn_records: workspace too small");
+  HMVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "attn_records: workspace must be 256-byte aligned");
+  return launch_records(p, a->kind, 1, a->workspace, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int hmvit_group_attn(const HmvitAttnArgs* a, void* stream) {
   AttnParams p;
   int rc = fill_attn_params(a, p); if (rc) return rc;

@@ -136,6 +136,19 @@ def group_attn(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, k, v
     return out
 
 
+def attn_records(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, workspace, key_mask=None):
+    """The fused attention's key-record pass on its own (see hmvit_attn_records): fills `workspace` for later
+    group_attn(..., workspace=workspace, records_valid=True) calls of the same geometry and kind."""
+    args = _lib.AttnArgs()
+    args.B, args.L, args.H, args.W, args.kind = B, L, H, W, kind
+    args.mode, args.record_len, args.cav_mask = mode.data_ptr(), record_len.data_ptr(), cav_mask.data_ptr()
+    args.T, args.cell = T.data_ptr(), float(cell)
+    args.key_mask = key_mask.data_ptr() if key_mask is not None else None
+    args.workspace, args.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    _lib.check(_lib.load().hmvit_attn_records(C.byref(args), _stream()))
+    return workspace
+
+
 # ---- backward pass -------------------------------------------------------------------------------
 def bwd_row_stats(x, stats, *, B, L, N, record_len, ego_only=False, eps=1e-5):
     """stats[a*N + tok] = (mean, rstd) of the 256 channels of x (cm fp32)."""

@@ -177,6 +177,10 @@ typedef struct {
 } HmvitAttnArgs;
 
 int hmvit_group_attn(const HmvitAttnArgs* args, void* stream);
+/* The key-record pass of HMVIT_ATTN_FUSED on its own (geometry fields, kind and workspace of `args`; q / k / v / out are not
+ * read): the poses do not change between the block iterations, so a caller that runs several attention stages of one kind
+ * computes the records once and passes records_valid = 1 afterwards (hmvit_fusion_forward does this for both kinds). */
+int hmvit_attn_records(const HmvitAttnArgs* args, void* stream);
 size_t hmvit_group_attn_workspace_bytes(int32_t impl, int32_t B, int32_t L, int32_t H, int32_t W);
 
 /* ---- stand-alone spatial warp and ROI mask (unit-parity surface) ------------------------------------

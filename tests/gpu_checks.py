@@ -461,9 +461,13 @@ def check_errors():
             net2(x[..., :12, :].contiguous().to(DEV), T.to(DEV), md.to(DEV), rl.to(DEV), mask.to(DEV))
         with pytest.raises(ValueError):
             net2(x, T, md, rl, mask)          # CPU tensors: no fallback
-    with pytest.raises(NotImplementedError):
-        net2.train()
-        net2(x.to(DEV), T.to(DEV), md.to(DEV), rl.to(DEV), mask.to(DEV))
+        with pytest.raises(ValueError):
+            net2(x.to(DEV), T[:, :1].contiguous().to(DEV), md.to(DEV), rl.to(DEV), mask.to(DEV))   # pairwise_t_matrix shape
+    bad_bias = p.HeteroFusion(cfg).eval().to(DEV)
+    with torch.no_grad():
+        bad_bias.hetero_fusion_block.window_attention.relative_position_bias_table.weight.fill_(100.0)
+        with pytest.raises(ValueError):
+            bad_bias(x.to(DEV), T.to(DEV), md.to(DEV), rl.to(DEV), mask.to(DEV))                   # bias table beyond +-40
     return {"ok": 1}
 
 
