@@ -36,8 +36,9 @@ HMVIT_DEVINL uint64_t umma_desc_sw128_mn(uint32_t smem_addr) { return umma_desc_
 
 // one visible key of a (scene, ego, group): 16 bytes
 struct KeyRec {
-  short x0, y0;                // (y0, x0) corner of the bilinear footprint in the source map
-  uint32_t w01, w23;           // tap weights as bf16 pairs: (w00, w01), (w10, w11); 0 = tap outside the map
+  uint32_t off;                // row offset of the footprint corner in the scene's K' / V' planes, in 16-byte units:
+                               // ((source j * N + y0 * W + x0) * 32); the corner lies in the map with both neighbours
+  uint32_t w01, w23;           // tap weights as bf16 pairs: (w00, w01), (w10, w11); 0 = tap that fell outside the map
   uint32_t meta;               // source j | slot << 8 | source type << 16 | relative-position offset << 24
 };
 static_assert(sizeof(KeyRec) == 16, "KeyRec must be 16 bytes");
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(256, 4) tap_records_kernel(const RecParams rp)
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
     const int e = it * 256 + threadIdx.x;
-    KeyRec r; r.x0 = 0; r.y0 = 0; r.w01 = 0; r.w23 = 0; r.meta = 0;
+    KeyRec r; r.off = 0; r.w01 = 0; r.w23 = 0; r.meta = 0;
     bool vis = false;
     if (e < nent) {
       const int j = e >> 6, tk = e & 63;
@@ -87,8 +88,15 @@ __global__ void __launch_bounds__(256, 4) tap_records_kernel(const RecParams rp)
         vis = warp_visible(sx, sy, p.H, p.W);
         if (p.key_mask != nullptr && p.key_mask[static_cast<size_t>(b * p.L + j) * N + rr * p.W + cc] == 0) vis = false;
         if (vis) {
-          const Taps tp = make_taps(sx, sy, p.H, p.W);
-          r.x0 = static_cast<short>(tp.x0); r.y0 = static_cast<short>(tp.y0);
+          Taps tp = make_taps(sx, sy, p.H, p.W);
+          // The footprint corner is moved INTO the map (a visible key has floor(sx) in [-1, W-1]): the taps that fell
+          // outside carry weight 0 and now read in-map rows, so the gather can load all four taps unconditionally
+          // (0 * finite == 0 exactly) -- no per-tap predicates, no zero-initialised destination registers.
+          if (tp.x0 < 0) { tp.x0 = 0; tp.w00 = tp.w01; tp.w10 = tp.w11; tp.w01 = 0.f; tp.w11 = 0.f; }
+          else if (tp.x0 > p.W - 2) { tp.x0 = p.W - 2; tp.w01 = tp.w00; tp.w11 = tp.w10; tp.w00 = 0.f; tp.w10 = 0.f; }
+          if (tp.y0 < 0) { tp.y0 = 0; tp.w00 = tp.w10; tp.w01 = tp.w11; tp.w10 = 0.f; tp.w11 = 0.f; }
+          else if (tp.y0 > p.H - 2) { tp.y0 = p.H - 2; tp.w10 = tp.w00; tp.w11 = tp.w01; tp.w00 = 0.f; tp.w01 = 0.f; }
+          r.off = static_cast<uint32_t>((j * N + tp.y0 * p.W + tp.x0) * 32);
           r.w01 = pack_bf16x2(tp.w00, tp.w01); r.w23 = pack_bf16x2(tp.w10, tp.w11);
           // a visible key always has a non-zero tap weight (the nearest in-range corner has weight >= 1/4)
         }
@@ -171,6 +179,12 @@ HMVIT_DEVINL uint4 ldg_nc_u4_if(const uint4* p, bool pred) {
       "@p ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
       : "l"(p), "r"(pred ? 1 : 0));
+  return v;
+}
+// unconditional 16-byte read-only global load, issued in program order
+HMVIT_DEVINL uint4 ldg_nc_u4_v(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
 HMVIT_DEVINL uint32_t hfma2_bf16_v(uint32_t a, uint32_t b, uint32_t c) {      // program-order variant of hfma2_bf16
@@ -514,8 +528,7 @@ __global__ void __launch_bounds__(FaCfg::THREADS, 2) fused_attn_kernel(const Fus
           const bool live = hw + n * 16 < nval;                    // past the item's visible keys: zero row, no loads
           w01 = live ? r1 : 0u; w23 = live ? r2 : 0u;
           meta = r3;
-          const int x0 = static_cast<short>(r0 & 0xffffu), y0 = static_cast<short>(r0 >> 16);
-          return static_cast<int>(((r3 & 0xffu) * N + y0 * p.W + x0) * 32);   // uint4 offset of the (y0, x0) row in the scene's planes
+          return static_cast<int>(r0);                             // uint4 offset of the footprint corner's row in the scene's planes
         };
         auto issue = [&](const uint4* base, int off, uint32_t wa, uint32_t wb, uint4 (&tv)[4]) {
           // a tap outside the map has weight 0 and is not loaded
