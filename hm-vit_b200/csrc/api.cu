@@ -325,32 +325,19 @@ static void fused_ws_split(const AttnParams& p, int nkinds, int which, void* ws,
   *nvis = reinterpret_cast<const int*>(static_cast<uint8_t*>(ws) + nkinds * align_up(per_kind * sizeof(KeyRec), 256)) + which * BL * G;
 }
 
-#ifndef HMVIT_FA2
-#define HMVIT_FA2 1          // 1: second form of the fused kernel (attn_fa2.cuh, default); 0: first form (attn_fused.cuh), tuning builds only
-#endif
 static int launch_fused_attn(const AttnParams& p, const KeyRec* rec, const int* nvis, cudaStream_t st) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(fused_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FaCfg::SMEM_BYTES);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(fused_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(fused_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa2Cfg::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(fused_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Fa2Cfg::SMEM_BYTES);
   });
   HMVIT_CHECK_CUDA(attr_err);
   FusedAttnParams fp;
   fp.a = p; fp.rec = rec; fp.nvis = nvis;
   const long long items = static_cast<long long>(p.B) * (p.ego_only ? 1 : p.L) * (p.H / 8) * (p.W / 8) * 2;
-#if HMVIT_FA2
   const long long cap = num_sms() & ~1;                        // one persistent CTA per SM, one head group each
   const int grid = static_cast<int>(items < cap ? items : cap);
   fused_attn2_kernel<<<grid, Fa2Cfg::THREADS, Fa2Cfg::SMEM_BYTES, st>>>(fp);
-#else
-  const long long cap = 2LL * num_sms();                       // 2 persistent CTAs per SM, one head group each
-  const int grid = static_cast<int>(items < cap ? items : cap);
-  fused_attn_kernel<<<grid, FaCfg::THREADS, FaCfg::SMEM_BYTES, st>>>(fp);
-#endif
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }

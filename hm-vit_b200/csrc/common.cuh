@@ -127,7 +127,7 @@ HMVIT_DEVINL void mbar_wait_sleepy(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity), "r"(200000u)
         : "memory");
-    if (++spins > (1u << 22)) { asm volatile("trap;"); }
+    if (++spins > (1u << 15)) { asm volatile("trap;"); }   // (each try may sleep up to the hint: ~seconds in total)
   } while (!ok);
 }
 
