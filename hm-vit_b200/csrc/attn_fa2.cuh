@@ -459,24 +459,36 @@ __global__ void __launch_bounds__(Fa2Cfg::THREADS, 1) fused_attn2_kernel(const F
         // value taps: 4 rows of 256 B each); two groups are in flight at any time (32 registers; 32 half-warps x 2 KB =
         // 64 KB per SM).
         uint4 kk[4], vv[4];
-        auto issue = [&](const uint4* base, uint32_t off, uint4 (&tv)[4]) {
+        // A key whose footprint is exactly one pixel (weights 1, 0, 0, 0: the ego's own keys, a third of all keys, and
+        // whole-cell poses) loads one row instead of four and adds it to the folded bias.
+        auto is_single = [](const uint4& r) { return r.y == 0x00003f80u && r.z == 0u; };
+        auto issue = [&](const uint4* base, const uint4& r, uint4 (&tv)[4]) {
           // all four taps are in the map (the record pass moved the corner; outside taps carry weight 0)
-          const uint4* r0 = base + off;
+          const uint4* r0 = base + r.x;
           const uint4* r1 = r0 + wrow;
           if (HMVIT_FA_DBG & 1) { tv[0] = tv[1] = tv[2] = tv[3] = make_uint4(0, 0, 0, 0); return; }
           tv[0] = ldg_nc_u4_v(r0);
-          tv[1] = ldg_nc_u4_v(r0 + 32);
-          tv[2] = ldg_nc_u4_v(r1);
-          tv[3] = ldg_nc_u4_v(r1 + 32);
+          if (!is_single(r)) {
+            tv[1] = ldg_nc_u4_v(r0 + 32);
+            tv[2] = ldg_nc_u4_v(r1);
+            tv[3] = ldg_nc_u4_v(r1 + 32);
+          }
         };
-        auto blend_store = [&](const uint4 (&tv)[4], uint32_t wa, uint32_t wb, uint32_t bias_addr, uint32_t daddr, bool live) {
+        auto blend_store = [&](const uint4 (&tv)[4], const uint4& r, uint32_t bias_addr, uint32_t daddr, bool live) {
           uint4 o = lds_u4_addr(bias_addr);
-          const uint32_t w2[4] = {__byte_perm(wa, wa, 0x1010), __byte_perm(wa, wa, 0x3232), __byte_perm(wb, wb, 0x1010),
-                                  __byte_perm(wb, wb, 0x3232)};
+          if (is_single(r)) {
+            const uint32_t one = 0x3f803f80u;
+            o.x = hfma2_bf16(one, tv[0].x, o.x); o.y = hfma2_bf16(one, tv[0].y, o.y);
+            o.z = hfma2_bf16(one, tv[0].z, o.z); o.w = hfma2_bf16(one, tv[0].w, o.w);
+          } else {
+            const uint32_t wa = r.y, wb = r.z;
+            const uint32_t w2[4] = {__byte_perm(wa, wa, 0x1010), __byte_perm(wa, wa, 0x3232), __byte_perm(wb, wb, 0x1010),
+                                    __byte_perm(wb, wb, 0x3232)};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            o.x = hfma2_bf16(w2[q], tv[q].x, o.x); o.y = hfma2_bf16(w2[q], tv[q].y, o.y);
-            o.z = hfma2_bf16(w2[q], tv[q].z, o.z); o.w = hfma2_bf16(w2[q], tv[q].w, o.w);
+            for (int q = 0; q < 4; ++q) {
+              o.x = hfma2_bf16(w2[q], tv[q].x, o.x); o.y = hfma2_bf16(w2[q], tv[q].y, o.y);
+              o.z = hfma2_bf16(w2[q], tv[q].z, o.z); o.w = hfma2_bf16(w2[q], tv[q].w, o.w);
+            }
           }
           if (!live) o = make_uint4(0, 0, 0, 0);                   // (selects, no branch)
           sts_u4_addr(daddr, o);
@@ -485,10 +497,11 @@ __global__ void __launch_bounds__(Fa2Cfg::THREADS, 1) fused_attn2_kernel(const F
         // coming from the shared-memory ring, either of the two the other way round (tap loads issued while parked on
         // kv_empty; slot released -- and refilled by the loader -- while parked) produced rare wrong key rows in single
         // tiles, although no value written or read moves across the wait (a build that prefetched the records into
-        // registers instead was exact with early loads but spilled: +30 %).  Not understood; the order that is
+        // registers instead was exact with early loads but spilled: +30 %; a consumer-side proxy fence behind the records wait
+        // did not help).  Not understood; the order that is
         // bit-reproducible over repeated runs is kept (tools/fa_stress.py).
         mbar_wait(&kv_empty[stage], ((tcnt / Cfg::STAGES) & 1u) ^ 1u);   // the tile STAGES back has been consumed
-        if (nkeys > 0) { issue(kbase, rc[0].x, kk); issue(vbase, rc[0].x, vv); }
+        if (nkeys > 0) { issue(kbase, rc[0], kk); issue(vbase, rc[0], vv); }
         __syncwarp();
         if (lane == 0) mbar_arrive(&rec_empty[rst]);               // records in registers
         if (gt == 0) FA_TS(1, ts_i++, 2);                           // stage free
@@ -498,10 +511,10 @@ __global__ void __launch_bounds__(Fa2Cfg::THREADS, 1) fused_attn2_kernel(const F
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
           if (n < nkeys) {                                         // (uniform)
-            const uint32_t wa = rc[n].y, wb = rc[n].z, meta = rc[n].w;
+            const uint32_t meta = rc[n].w;
             const uint32_t tjo = ((meta >> 16) & 1u) * 512u, slot = (meta >> 8) & 63u;
             const bool live = hw + n * 32 < nval;                  // padding row: key row repeated, value row zero
-            blend_store(kk, wa, wb, kvb_te + tjo, dst + n * 4096, true);
+            blend_store(kk, rc[n], kvb_te + tjo, dst + n * 4096, true);
             if (u16 < 8) {
               // one-hot column block of the key (1.0 fp16 at its group slot): copied from the static table
               sts_u4_addr(dst + 32768 + n * 4096, lds_u4_addr(oh_u + slot * 128u));
@@ -509,9 +522,9 @@ __global__ void __launch_bounds__(Fa2Cfg::THREADS, 1) fused_attn2_kernel(const F
               // live indicator (bf16, K-major [16 x keys], row 0): 1.0 for a visible key, 0 for a padding row
               asm volatile("st.shared.u16 [%0], %1;" ::"r"(sbase + 40960 + (hw + n * 32) * 2), "h"(static_cast<uint16_t>(live ? 0x3f80 : 0)) : "memory");
             }
-            if (n + 1 < nkeys) issue(kbase, rc[1].x, kk);
-            blend_store(vv, wa, wb, kvb_te + tjo + 256, dst + 16384 + n * 4096, live);
-            if (n + 1 < nkeys) issue(vbase, rc[1].x, vv);
+            if (n + 1 < nkeys) issue(kbase, rc[1], kk);
+            blend_store(vv, rc[n], kvb_te + tjo + 256, dst + 16384 + n * 4096, live);
+            if (n + 1 < nkeys) issue(vbase, rc[1], vv);
             if (gt == 0) FA_TS(1, ts_i++, 5 + n);                  // key n of the half-warp stored
           }
         }
