@@ -7,10 +7,11 @@ from . import _lib, ops, training  # noqa: F401
 from .fusion import (HeteroAttention, HeteroFeedForward, HeteroFusion, HeteroFusionBlock,  # noqa: F401
                      HeteroLayerNorm, HeteroPreNormResidual, SpatialTransformation,
                      get_roi_and_cav_mask, regroup)
+from .decoder import HeteroDecoder, NaiveDecoder  # noqa: F401
 from .build import build_extension  # noqa: F401
 from .sharding import max_over_ranks, scene_shard  # noqa: F401
 from .distributed import FlatGradAllReduce  # noqa: F401
 
 __all__ = ["HeteroFusion", "HeteroFusionBlock", "HeteroAttention", "HeteroLayerNorm", "HeteroFeedForward",
            "HeteroPreNormResidual", "SpatialTransformation", "get_roi_and_cav_mask", "regroup",
-           "build_extension", "ops", "training", "FlatGradAllReduce"]
+           "HeteroDecoder", "NaiveDecoder", "build_extension", "ops", "training", "FlatGradAllReduce"]

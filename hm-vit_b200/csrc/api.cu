@@ -11,6 +11,7 @@
 #include "dropout.cuh"
 #include "chain.cuh"
 #include "qkv.cuh"
+#include "decoder.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -770,6 +771,68 @@ extern "C" int hmvit_group_attn_bwd(const HmvitAttnBwdArgs* a, void* stream) {
   p.dq = a->dq; p.dk = a->dk; p.dv = a->dv; p.dbk = a->dbk; p.dbv = a->dbv; p.dbias_table = a->dbias_table;
   dim3 grid((a->H / 8) * (a->W / 8) * 2, a->B * a->L);
   group_attn_bwd_kernel<<<grid, AttnBwdCfg::THREADS, AttnBwdCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// detection decoder (csrc/decoder.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t hmvit_decoder_workspace_bytes(int32_t B, int32_t H, int32_t W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return 2 * align_up(static_cast<size_t>(B) * H * W * 256 * sizeof(__half), 1024);      // two fp16 pixel-row maps (ping-pong)
+}
+static int make_act_tmap(CUtensorMap* map, const void* act, int B, int H, int W) {
+  std::call_once(g_encode_once, load_encode);
+  if (!g_encode) return fail(HMVIT_ERR_CUDA, "hmvit: cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {256, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[3] = {512, static_cast<cuuint64_t>(W) * 512, static_cast<cuuint64_t>(H) * W * 512};
+  cuuint32_t box[4] = {64, DecCfg::TW, DecCfg::TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(act), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);      // out-of-range pixels read as zeros: the convolution's padding
+  if (r != CUDA_SUCCESS) return fail(HMVIT_ERR_CUDA, "hmvit: cuTensorMapEncodeTiled (activations) failed (" + std::to_string(int(r)) + ")");
+  return HMVIT_OK;
+}
+extern "C" int hmvit_decoder_forward(const HmvitDecoderArgs* a, void* stream) {
+  HMVIT_CHECK_ARG(a != nullptr, "decoder_forward: null args");
+  HMVIT_CHECK_ARG(a->B > 0 && a->H > 0 && a->W > 0 && a->B <= 65535, "decoder_forward: bad shape");
+  HMVIT_CHECK_ARG(a->H % 8 == 0 && a->W % 8 == 0, "decoder_forward: H and W must be divisible by 8");
+  HMVIT_CHECK_ARG(a->num_convs >= 1 && a->num_convs <= 16, "decoder_forward: num_convs out of range");
+  HMVIT_CHECK_ARG(a->anchor_number >= 1 && 8 * a->anchor_number <= kDecMaxOut, "decoder_forward: anchor_number must be in 1..4");
+  HMVIT_CHECK_ARG(a->ego_mode && a->x && a->conv_w && a->conv_b && a->head_w && a->head_b && a->psm && a->rm, "decoder_forward: null pointer");
+  HMVIT_CHECK_ARG(a->workspace != nullptr && a->workspace_bytes >= hmvit_decoder_workspace_bytes(a->B, a->H, a->W), "decoder_forward: workspace too small");
+  HMVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(a->workspace) & 1023) == 0 && (reinterpret_cast<uintptr_t>(a->conv_w) & 127) == 0,
+                  "decoder_forward: workspace must be 1024-byte, conv_w 128-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg::SMEM_BYTES);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  const int N = a->H * a->W;
+  const size_t map_bytes = align_up(static_cast<size_t>(a->B) * N * 256 * sizeof(__half), 1024);
+  __half* act[2] = {static_cast<__half*>(a->workspace), reinterpret_cast<__half*>(static_cast<uint8_t*>(a->workspace) + map_bytes)};
+  nchw_to_nhwc_f16_kernel<<<dim3((N + 63) / 64, a->B), 256, 0, st>>>(a->x, act[0], N);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  const int tiles = ((a->W + DecCfg::TW - 1) / DecCfg::TW) * ((a->H + DecCfg::TH - 1) / DecCfg::TH);
+  for (int l = 0; l < a->num_convs; ++l) {
+    CUtensorMap mx, mw;
+    int rc = make_act_tmap(&mx, act[l & 1], a->B, a->H, a->W); if (rc) return rc;
+    rc = make_weight_tmap(&mw, static_cast<const __half*>(a->conv_w) + static_cast<size_t>(l) * 2 * 9 * 256 * 256, 2LL * 9 * 256, 2, 256, true);
+    if (rc) return rc;
+    ConvParams cp;
+    cp.B = a->B; cp.H = a->H; cp.W = a->W; cp.ego_mode = a->ego_mode; cp.bias = a->conv_b + static_cast<size_t>(l) * 2 * 256;
+    cp.out = act[(l + 1) & 1];
+    conv3x3_kernel<<<dim3(tiles, a->B), DecCfg::THREADS, DecCfg::SMEM_BYTES, st>>>(mx, mw, cp);
+    HMVIT_CHECK_CUDA(cudaGetLastError());
+  }
+  HeadsParams hp;
+  hp.B = a->B; hp.N = N; hp.n_cls = a->anchor_number; hp.n_reg = 7 * a->anchor_number; hp.ego_mode = a->ego_mode;
+  hp.x = act[a->num_convs & 1]; hp.w = a->head_w; hp.bias = a->head_b; hp.psm = a->psm; hp.rm = a->rm;
+  det_heads_kernel<<<dim3((N + 127) / 128, a->B), 128, 0, st>>>(hp);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }

@@ -252,3 +252,24 @@ def fusion_launch_count(num_iters, head, skip_dead=True, attn_impl=None) -> int:
     """Kernel launches of one hmvit_fusion_forward.  With skip_dead (the module default) the head runs inside the last
     stage's chain launch instead of a launch of its own."""
     return int(_lib.load().hmvit_fusion_launch_count(num_iters, (2 if skip_dead else 1) if head else 0, _IMPL[attn_impl]))
+
+
+def decoder_workspace_bytes(B, H, W):
+    return int(_lib.load().hmvit_decoder_workspace_bytes(B, H, W))
+
+
+def decoder_forward(*, x, ego_mode, conv_w, conv_b, head_w, head_b, anchor_number, psm, rm, workspace):
+    """HeteroDecoder.forward(use_upsample=False) on the ego's fused feature x (B, 256, H, W) fp32: BatchNorm-folded fp16
+    convolution weights [num_convs][2][9][256][256], fp32 biases / head weights (see include/hmvit_b200.h)."""
+    args = _lib.DecoderArgs()
+    B, _, H, W = x.shape
+    args.B, args.H, args.W = B, H, W
+    args.num_convs = conv_w.shape[0]
+    args.anchor_number = anchor_number
+    args.ego_mode, args.x = ego_mode.data_ptr(), x.data_ptr()
+    args.conv_w, args.conv_b = conv_w.data_ptr(), conv_b.data_ptr()
+    args.head_w, args.head_b = head_w.data_ptr(), head_b.data_ptr()
+    args.psm, args.rm = psm.data_ptr(), rm.data_ptr()
+    args.workspace, args.workspace_bytes = workspace.data_ptr(), workspace.numel()
+    _lib.check(_lib.load().hmvit_decoder_forward(C.byref(args), _stream()))
+    return psm, rm

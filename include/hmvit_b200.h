@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMVIT_ABI_VERSION 5
+#define HMVIT_ABI_VERSION 6
 
 /* error codes */
 #define HMVIT_OK 0
@@ -314,6 +314,32 @@ typedef struct {
   float* dbk; float* dbv; float* dbias_table;
 } HmvitAttnBwdArgs;
 int hmvit_group_attn_bwd(const HmvitAttnBwdArgs* args, void* stream);
+
+/* ---- detection decoder on the ego's fused feature --------------------------------
+ * Replaces HeteroDecoder.forward(x, mode, use_upsample=False)
+ *   opencood/models/sub_modules/hetero_decoder.py:42-74 (modality of the ego picks the camera / lidar weights),
+ *   opencood/models/sub_modules/naive_decoder.py:63-92 (2 * num_layer x conv3x3 256->256 + BatchNorm + ReLU),
+ *   the 1x1 cls / reg heads hetero_decoder.py:33-40, 62-70
+ * as called from BevformerPointPillarHetero.forward (opencood/models/bevformer_point_pillar_hetero.py:125-126).
+ * Eval-mode BatchNorm is folded into the convolution weights / bias by the caller (hm-vit_b200/decoder.py).
+ * Kernels: csrc/decoder.cuh (TMA-shifted implicit-GEMM convolution on tcgen05, fp16 operands, fp32 accumulate). */
+typedef struct {
+  int32_t B, H, W;            /* scenes, BEV map; H, W divisible by 8 */
+  int32_t num_convs;          /* 2 * num_layer convolutions */
+  int32_t anchor_number;      /* A: psm has A channels, rm 7 A; 8 A <= 32 */
+  const int32_t* ego_mode;    /* [B] 0 = camera, 1 = lidar (mode[:, 0]) */
+  const float* x;             /* fp32 (B, 256, H, W): output of hmvit_fusion_forward */
+  const void* conv_w;         /* fp16 [num_convs][2 (type)][9 (tap ky*3+kx)][256 out][256 in], BatchNorm folded */
+  const float* conv_b;        /* fp32 [num_convs][2][256] folded bias */
+  const float* head_w;        /* fp32 [2][8 A][256]: cls_head rows, then reg_head rows */
+  const float* head_b;        /* fp32 [2][8 A] */
+  float* psm;                 /* fp32 (B, A, H, W) */
+  float* rm;                  /* fp32 (B, 7 A, H, W) */
+  void* workspace;            /* hmvit_decoder_workspace_bytes(B, H, W), 1024-byte aligned */
+  size_t workspace_bytes;
+} HmvitDecoderArgs;
+size_t hmvit_decoder_workspace_bytes(int32_t B, int32_t H, int32_t W);
+int hmvit_decoder_forward(const HmvitDecoderArgs* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -362,6 +362,59 @@ def check_logits_golden():
     return res
 
 
+def check_decoder_vs_oracle():
+    """HeteroDecoder on the GPU (TMA-shifted implicit-GEMM convolutions, fp16 operands) against the fp32 restatement of
+    hetero_decoder.py:42-74 / naive_decoder.py:63-92 on a random ego feature at the BASELINE map size, mixed ego
+    modalities (both weight sets in one launch).  Stated tolerance: rel-L2 <= 1e-3 per tensor."""
+    torch.manual_seed(7)
+    B, H, W = 3, 48, 176
+    PD = O.synth_decoder_state_dict(11)
+    x = torch.randn(B, 256, H, W)
+    mode = torch.tensor([[1, 0], [0, 1], [1, 1]], dtype=torch.int32)
+    dec = pkg().HeteroDecoder({"input_dim": 256, "num_layer": 2, "num_ch_dec": [256, 256], "anchor_number": 2}).eval()
+    dec.load_state_dict(PD, strict=True)
+    dec = dec.to(DEV)
+    with torch.no_grad():
+        psm, rm = dec(x.to(DEV).unsqueeze(1), mode.to(DEV), use_upsample=False)
+    rp, rr = O.hetero_decoder(x, mode[:, 0], PD)
+    res = {"psm_rel_l2": rel_l2(psm.cpu(), rp), "rm_rel_l2": rel_l2(rm.cpu(), rr),
+           "psm_max_rel": max_rel(psm.cpu(), rp), "rm_max_rel": max_rel(rm.cpu(), rr)}
+    assert res["psm_rel_l2"] < 1e-3 and res["rm_rel_l2"] < 1e-3, res
+    # a map whose width is not a multiple of the 16-pixel tile: clipped tiles, zero padding through the TMA bounds
+    x2 = torch.randn(1, 256, 16, 24)
+    with torch.no_grad():
+        psm2, rm2 = dec(x2.to(DEV), mode[:1].to(DEV), use_upsample=False)
+    rp2, rr2 = O.hetero_decoder(x2, mode[:1, 0], PD)
+    res["clipped_psm_rel_l2"], res["clipped_rm_rel_l2"] = rel_l2(psm2.cpu(), rp2), rel_l2(rm2.cpu(), rr2)
+    assert res["clipped_psm_rel_l2"] < 1e-3 and res["clipped_rm_rel_l2"] < 1e-3, res
+    return res
+
+
+def check_decoder_logits_golden():
+    """psm / rm produced END TO END on the GPU (hmvit_fusion_forward -> hmvit_decoder_forward) against the reference
+    pipeline's logits (tests/golden/logits_c256.npz: HeteroFusion -> HeteroDecoder of the unmodified reference).
+    Stated tolerance: rel-L2 <= 1e-3 per tensor (north_star: detection-head logits)."""
+    g = np.load(os.path.join(GOLDEN, "fusion_c256.npz"))
+    gl = np.load(os.path.join(GOLDEN, "logits_c256.npz"))
+    C, B, L, H, W, seed = (int(v) for v in g["meta"][:6])
+    cfg = O.default_config(input_dim=C)
+    P = O.synth_state_dict(cfg, seed)
+    PD = O.synth_decoder_state_dict(seed + 1)
+    x, T, mode, rl, mask = O.synth_inputs(B, L, C, H, W, g["record_len"].tolist(), seed + 100,
+                                          tx=float(g["meta"][6]), ty=float(g["meta"][7]))
+    net = pkg().HeteroFusion(cfg).eval()
+    net.load_state_dict(P, strict=True)
+    dec = pkg().HeteroDecoder({"input_dim": 256, "num_layer": 2, "num_ch_dec": [256, 256], "anchor_number": 2}).eval()
+    dec.load_state_dict(PD, strict=True)
+    net, dec = net.to(DEV), dec.to(DEV)
+    with torch.no_grad():
+        y = net(x.to(DEV), T.to(DEV), mode.to(DEV), rl.to(DEV), mask.to(DEV))
+        psm, rm = dec(y.unsqueeze(1), mode.to(DEV), use_upsample=False)
+    res = {"psm_rel_l2": rel_l2(psm.cpu(), torch.from_numpy(gl["psm"])), "rm_rel_l2": rel_l2(rm.cpu(), torch.from_numpy(gl["rm"]))}
+    assert res["psm_rel_l2"] < 1e-3 and res["rm_rel_l2"] < 1e-3, res
+    return res
+
+
 def check_fusion_config5_scene():
     """BASELINE config 5 shape, one scene: 7 agents (LiDAR ego + 6 camera collaborators), 256x96x352."""
     cfg, P, inp, y, net = _fusion_case(1, 7, 96, 352, [7], seed=1239, mode=[[1, 0, 0, 0, 0, 0, 0]], tx=100.0, ty=30.0)
@@ -490,6 +543,8 @@ CHECKS = {
     "fusion_small": check_fusion_small,
     "fusion_golden": check_fusion_golden,
     "logits_golden": check_logits_golden,
+    "decoder_vs_oracle": check_decoder_vs_oracle,
+    "decoder_logits_golden": check_decoder_logits_golden,
     "fusion_config1": check_fusion_config1,
     "fusion_config2_scene": check_fusion_config2_scene,
     "fusion_properties": check_fusion_properties,

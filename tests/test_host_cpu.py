@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(pkg._lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert pkg._lib.load().hmvit_abi_version() == pkg._lib.ABI_VERSION == 5
+    assert pkg._lib.load().hmvit_abi_version() == pkg._lib.ABI_VERSION == 6
 
 
 def test_state_dict_keys_match_reference_spec():
@@ -131,3 +131,43 @@ def test_bench_flop_count_matches_survey():
     skipped = (Lv - 1) * N * (2 * C * C + 2 * (Lv * 64) * 2 * C + 2 * C * C + 4 * C * C)
     assert b.scene_flops(5, 2, True) == b.scene_flops(5) - skipped
     assert abs(b.scene_flops(2) / 1e9 - 64.2) < 0.1                      # config 1 figure of the survey
+
+
+def test_decoder_state_dict_keys_and_batchnorm_folding():
+    """HeteroDecoder mirror: state_dict keys / shapes of the reference (oracle spec, which loads strict=True into the
+    reference in tests/golden/make_golden.py), and the BatchNorm folding the kernels consume is exact: convolutions with
+    the folded weights reproduce the restatement of hetero_decoder.py:42-74 in fp32."""
+    import torch.nn.functional as F
+    pkg = hmvit_loader.load()
+    params = {"input_dim": 256, "num_layer": 2, "num_ch_dec": [256, 256], "anchor_number": 2}
+    dec = pkg.HeteroDecoder(params).eval()
+    spec = O.decoder_state_spec()
+    sd = dec.state_dict()
+    assert list(sd.keys()) == [k for k, _ in spec]
+    for k, shape in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+    PD = O.synth_decoder_state_dict(3)
+    dec.load_state_dict(PD, strict=True)
+    pk = dec.packed()
+    assert pk["conv_w"].shape == (4, 2, 9, 256, 256) and pk["conv_w"].dtype == torch.float16
+    assert pk["conv_b"].shape == (4, 2, 256) and pk["head_w"].shape == (2, 16, 256) and pk["head_b"].shape == (2, 16)
+    torch.manual_seed(0)
+    x = torch.randn(2, 256, 8, 8)
+    ego_mode = torch.tensor([1, 0])
+    rp, rr = O.hetero_decoder(x, ego_mode, PD)
+    for b in range(2):
+        t = int(ego_mode[b])
+        nd = dec.lidar_decoder if t == 1 else dec.camera_decoder
+        w, bias = nd.folded()
+        y = x[b:b + 1]
+        for l in range(4):
+            y = F.relu(F.conv2d(y, w[l].view(3, 3, 256, 256).permute(2, 3, 0, 1), bias[l], padding=1))
+        out = F.conv2d(y, pk["head_w"][t].view(16, 256, 1, 1), pk["head_b"][t])
+        assert float((out[:, :2] - rp[b:b + 1]).norm() / rp[b:b + 1].norm()) < 1e-5
+        assert float((out[:, 2:] - rr[b:b + 1]).norm() / rr[b:b + 1].norm()) < 1e-5
+    with pytest.raises(NotImplementedError):
+        dec(x, torch.ones(2, 1), use_upsample=True)
+    with pytest.raises(ValueError):
+        dec(x, torch.ones(2, 1), use_upsample=False)           # CPU tensors: no fallback
+    with pytest.raises(ValueError):
+        pkg.HeteroDecoder({"input_dim": 128, "num_layer": 2, "num_ch_dec": [128, 128], "anchor_number": 2})
