@@ -469,3 +469,52 @@ def hetero_decoder(x: Tensor, ego_mode: Tensor, P: Dict[str, Tensor], num_layer:
         psm.append(F.conv2d(y, P[f"{mod}_cls_head.weight"], P[f"{mod}_cls_head.bias"]))
         rm.append(F.conv2d(y, P[f"{mod}_reg_head.weight"], P[f"{mod}_reg_head.bias"]))
     return torch.cat(psm, 0), torch.cat(rm, 0)
+
+
+# ----------------------------------------------------------------------------------------------
+# model glue: restatement of base_camera_lidar_intermediate.py, loops as in the reference
+# ----------------------------------------------------------------------------------------------
+def unpad_mode_encoding(mode: Tensor, record_len: Tensor) -> Tensor:
+    """base_camera_lidar_intermediate.py:68-73."""
+    return torch.cat([mode[i, :int(record_len[i])] for i in range(mode.shape[0])], dim=0)
+
+
+def combine_features(camera_feature, lidar_feature, mode: Tensor, record_len: Tensor) -> Tensor:
+    """base_camera_lidar_intermediate.py:81-99."""
+    if mode.dim() == 2:
+        mode = unpad_mode_encoding(mode, record_len)
+    out, cc, lc = [], 0, 0
+    for i in range(len(mode)):
+        if mode[i] == 0:
+            out.append(camera_feature[cc]); cc += 1
+        elif mode[i] == 1:
+            out.append(lidar_feature[lc]); lc += 1
+        else:
+            raise ValueError("Mode but be either 1 or 0")
+    return torch.stack(out, dim=0)
+
+
+def extract_lidar_input(processed_lidar: Dict[str, Tensor], mode_unpack: Tensor) -> Dict[str, Tensor]:
+    """base_camera_lidar_intermediate.py:31-66 (on a copy of voxel_coords: the reference renumbers in place)."""
+    coords = processed_lidar['voxel_coords'].clone()
+    feats, cs, nums, count = [], [], [], 0
+    for i in range(len(mode_unpack)):
+        if mode_unpack[i] != 1:
+            continue
+        m = processed_lidar['voxel_coords'][:, 0] == i
+        c = coords[m, :].clone()
+        c[:, 0] = count
+        cs.append(c)
+        feats.append(processed_lidar['voxel_features'][m, :])
+        nums.append(processed_lidar['voxel_num_points'][m])
+        count += 1
+    return {'voxel_features': torch.cat(feats, 0), 'voxel_coords': torch.cat(cs, 0), 'voxel_num_points': torch.cat(nums, 0)}
+
+
+def detector_forward_features(camera_features, lidar_features, mode, record_len, pairwise_t_matrix, P, PD, cfg):
+    """bevformer_point_pillar_hetero.py:113-134 behind the encoders: combine -> regroup -> HeteroFusion -> HeteroDecoder."""
+    mode = mode.to(torch.int)
+    x = combine_features(camera_features, lidar_features, unpad_mode_encoding(mode, record_len), record_len)
+    x, mask = regroup(x, record_len, mode.shape[1])
+    fused = hetero_fusion(x, pairwise_t_matrix, mode, record_len, mask, P, cfg)
+    return hetero_decoder(fused, mode[:, 0], PD)

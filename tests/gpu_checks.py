@@ -415,6 +415,39 @@ def check_decoder_logits_golden():
     return res
 
 
+def check_model_glue():
+    """Model glue behind the encoders (bevformer_point_pillar_hetero.py:113-134): per-modality BEV features -> combine ->
+    regroup -> fusion -> decoder -> psm / rm on the GPU, against the loop restatement of the same pipeline on the CPU
+    oracle.  Mixed modalities, a ragged batch.  Stated tolerance for this COMPOSED case: rel-L2 <= 2e-3 per tensor -- each
+    stage has its own 1e-3 bar against the oracle on identical inputs (fusion checks; decoder_vs_oracle), and the logits of
+    the reference-pinned case meet 1e-3 end to end (decoder_logits_golden); here the two stages' errors add on unnormalised
+    random features (measured 1.5e-3 / 1.0e-3)."""
+    from importlib import import_module
+    M = import_module("hmvit_b200.model")
+    torch.manual_seed(5)
+    B, L, H, W = 2, 3, 16, 24
+    mode = torch.tensor([[1, 0, 1], [0, 1, 0]], dtype=torch.int32)
+    rl = torch.tensor([3, 2])
+    cfgf = O.default_config()
+    P, PD = O.synth_state_dict(cfgf, 21), O.synth_decoder_state_dict(22)
+    _, T, _, _, _ = O.synth_inputs(B, L, 256, H, W, rl.tolist(), 23)
+    mu = O.unpad_mode_encoding(mode, rl)
+    cam = torch.randn(int((mu == 0).sum()), 256, H, W)
+    lid = torch.randn(int((mu == 1).sum()), 256, H, W)
+    cfg = {"max_cav": L, "compression": 0, "anchor_number": 2, "spatial_transform": cfgf["spatial_transform"],
+           "hetero_fusion": cfgf, "hetero_decoder": {"input_dim": 256, "num_layer": 2, "num_ch_dec": [256, 256], "anchor_number": 2}}
+    net = M.BevformerPointPillarHetero(cfg).eval()
+    net.fusion_net.load_state_dict(P, strict=True)
+    net.decoder.load_state_dict(PD, strict=True)
+    net = net.to(DEV)
+    with torch.no_grad():
+        out = net.forward_features(cam.to(DEV), lid.to(DEV), mode.to(DEV), rl.to(DEV), T.to(DEV))
+    rp, rr = O.detector_forward_features(cam, lid, mode, rl, T, P, PD, cfgf)
+    res = {"psm_rel_l2": rel_l2(out["psm"].cpu(), rp), "rm_rel_l2": rel_l2(out["rm"].cpu(), rr)}
+    assert res["psm_rel_l2"] < 2e-3 and res["rm_rel_l2"] < 2e-3, res
+    return res
+
+
 def check_fusion_config5_scene():
     """BASELINE config 5 shape, one scene: 7 agents (LiDAR ego + 6 camera collaborators), 256x96x352."""
     cfg, P, inp, y, net = _fusion_case(1, 7, 96, 352, [7], seed=1239, mode=[[1, 0, 0, 0, 0, 0, 0]], tx=100.0, ty=30.0)
@@ -545,6 +578,7 @@ CHECKS = {
     "logits_golden": check_logits_golden,
     "decoder_vs_oracle": check_decoder_vs_oracle,
     "decoder_logits_golden": check_decoder_logits_golden,
+    "model_glue": check_model_glue,
     "fusion_config1": check_fusion_config1,
     "fusion_config2_scene": check_fusion_config2_scene,
     "fusion_properties": check_fusion_properties,

@@ -171,3 +171,40 @@ def test_decoder_state_dict_keys_and_batchnorm_folding():
         dec(x, torch.ones(2, 1), use_upsample=False)           # CPU tensors: no fallback
     with pytest.raises(ValueError):
         pkg.HeteroDecoder({"input_dim": 128, "num_layer": 2, "num_ch_dec": [128, 128], "anchor_number": 2})
+
+
+def test_model_glue_matches_reference_restatement():
+    """combine_features / unpad_mode_encoding / extract_lidar_input of the model glue (vectorised) against the loop
+    restatement of base_camera_lidar_intermediate.py:31-99; the config keys of the shipped yaml construct the model."""
+    pkg = hmvit_loader.load()
+    from importlib import import_module
+    M = import_module("hmvit_b200.model")
+    torch.manual_seed(3)
+    mode = torch.tensor([[1, 0, 0, 1, 0], [0, 1, 1, 0, 0], [1, 1, 0, 0, 0]])
+    rl = torch.tensor([4, 2, 5])
+    mu = M.unpad_mode_encoding(mode, rl)
+    assert torch.equal(mu, O.unpad_mode_encoding(mode, rl))
+    n_cam, n_lid = int((mu == 0).sum()), int((mu == 1).sum())
+    cam, lid = torch.randn(n_cam, 4, 2, 3), torch.randn(n_lid, 4, 2, 3)
+    assert torch.equal(M.combine_features(cam, lid, mode, rl), O.combine_features(cam, lid, mode, rl))
+    x = torch.randn(3, 5, 2)
+    assert torch.equal(M.unpad_features(x, rl), torch.cat([x[i, :int(rl[i])] for i in range(3)]))
+    with pytest.raises(ValueError):
+        M.combine_features(cam[:1], lid, mode, rl)
+    nv = 57
+    pl = {"voxel_features": torch.randn(nv, 32, 4), "voxel_coords": torch.randint(0, 40, (nv, 4)),
+          "voxel_num_points": torch.randint(1, 32, (nv,))}
+    pl["voxel_coords"][:, 0] = torch.randint(0, int(rl.sum()), (nv,))
+    got = M.BevformerPointPillarHetero.extract_lidar_input({"processed_lidar": pl}, mu)["processed_lidar"]
+    want = O.extract_lidar_input(pl, mu)
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    cfg = {"max_cav": 5, "compression": 0, "anchor_number": 2,
+           "spatial_transform": O.default_config()["spatial_transform"], "hetero_fusion": O.default_config(),
+           "hetero_decoder": {"input_dim": 256, "num_layer": 2, "num_ch_dec": [256, 256], "anchor_number": 2}}
+    net = M.BevformerPointPillarHetero(cfg)
+    keys = list(net.state_dict().keys())
+    assert any(k.startswith("fusion_net.hetero_fusion_block.") for k in keys) and "decoder.camera_cls_head.weight" in keys
+    assert "cls_head.weight" in keys and "reg_head.bias" in keys
+    with pytest.raises(NotImplementedError):
+        net({"mode": mode, "record_len": rl, "pairwise_t_matrix": None})      # no encoders passed in
