@@ -196,6 +196,41 @@ def ragged_variant(net, dev, batch, steps, warmup):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def detector_variant(pkg, net, dev, inp, steps, warmup):
+    """the same step followed by the detection decoder on the ego's fused feature (HeteroDecoder with
+    use_upsample=False: 4 x conv3x3 256->256 + heads = 39.9 GF per scene), i.e. fused features -> psm / rm on the GPU.
+    Device-resident, CUDA events.  A reported side figure, never the headline."""
+    try:
+        torch.manual_seed(7)                                      # random-init weights of the architecture (nn defaults)
+        dec = pkg.HeteroDecoder({"input_dim": 256, "num_layer": 2, "num_ch_dec": [256, 256], "anchor_number": 2}).eval()
+        dec = dec.to(dev)
+        mode = inp[2]
+
+        def step():
+            y = net(*inp)
+            return dec(y, mode, use_upsample=False)
+        y = net(*inp)
+        for _ in range(max(2, warmup)):
+            step()
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        for _ in range(steps):
+            step()
+        e[1].record()
+        for _ in range(steps):
+            dec(y, mode, use_upsample=False)
+        e[2].record()
+        torch.cuda.synchronize()
+        ms, ms_dec = e[0].elapsed_time(e[1]) / steps, e[1].elapsed_time(e[2]) / steps
+        B_, _, H_, W_ = y.shape
+        gf = (4 * 2 * 9 * 256 * 256 + 2 * 16 * 256) * H_ * W_ * B_ / 1e9
+        return {"workload": "fusion forward + HeteroDecoder (psm, rm) per step", "ms_per_step": ms, "scenes_per_s": B_ / (ms * 1e-3),
+                "decoder_ms_per_step": ms_dec, "decoder_gflop_per_scene": gf / B_, "decoder_tflops": gf / ms_dec}
+    except Exception as e_:      # noqa: BLE001
+        return {"error": f"{type(e_).__name__}: {e_}"[:300]}
+
+
 def stress_variant(pkg, net, dev, steps=3, warmup=1):
     """BASELINE configs[4] (stress): 32 scenes x 7 agents (LiDAR ego + 6 camera collaborators), 256x96x352, one step =
     one forward over the whole batch on one GPU (the reference would materialise 54 GB of warped pairs per call).  A
@@ -479,6 +514,7 @@ def main():
         th.join(timeout=2)
         kern = kernel_breakdown(pkg, net, dev_in) if rank == 0 else None
         ragged = ragged_variant(net, dev, Bq, args.steps, args.warmup) if rank == 0 and world == 1 else None
+        detector = detector_variant(pkg, net, dev, dev_in, args.steps, args.warmup) if rank == 0 and world == 1 else None
     stress = None
     if not args.no_stress and rank == 0 and world == 1:
         stress = stress_variant(pkg, net, dev)
@@ -583,6 +619,8 @@ def main():
         line["stress_variant"] = stress
     if ragged is not None:
         line["ragged_variant"] = ragged
+    if detector is not None:
+        line["detector_variant"] = detector
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_arm(3, 1)[0]
     elif world == 1:
