@@ -560,10 +560,12 @@ def main():
         per_dead = (2 * Lv + 2) * N_TOK * C * 2 * Bq
         alg = (per_full * (launches - 1) + per_dead) / launches if net.skip_dead_queries else per_full
         achieved = alg / (kern[dom]["ms_per_launch"] * 1e-3) / 1e9
-        traffic = ncu_traffic("fused_attn_kernel")
+        traffic = ncu_traffic("fused_attn2_kernel")
         note = ("algorithmic bytes = Q + K' + V' read once + O written, bf16 (DESIGN.md); one persistent tcgen05 kernel "
-                "(fused_attn_kernel) per stage, the blended key / value tiles stay in shared memory; the key-record pass "
-                "(tap_records_kernel) runs once per forward, not per stage; tensor work 2*2*Lv*N*(Lv*64)*2C FLOP per scene")
+                "(fused_attn2_kernel, csrc/attn_fa2.cuh) per stage, the blended key / value tiles stay in shared memory; the "
+                "key-record pass (tap_records_kernel) runs once per forward, not per stage; traffic = DRAM bytes per launch of "
+                "the ncu --set full capture of this command averaged over the 3 full + 1 ego-only launches of a step, like "
+                "`achieved` (profiles/r2_traffic.json); tensor work 2*2*Lv*N*(Lv*64)*2C FLOP per scene")
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                 "traffic": traffic, "peak_source": src, "note": note}
     else:
