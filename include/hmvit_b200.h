@@ -137,11 +137,13 @@ int hmvit_ffn_head(const HmvitHeadArgs* args, void* stream);
  * and the warp / ROI-mask helpers it calls
  *   opencood/models/sub_modules/torch_transformation_utils.py:11-134, 254-355.
  * Three implementations of the same contract, selected explicitly (no environment switches):
- *   HMVIT_ATTN_FUSED   default: a key-record pass (fp64 source-pixel maps, bit-exact ROI visibility, compaction of the
- *                      visible keys; csrc/attn_fused.cuh tap_records_kernel) + ONE persistent warp-specialised tcgen05
- *                      kernel whose gather warps blend the projected K' / V' taps straight into shared-memory operand
- *                      tiles (fused_attn_kernel).  Needs a workspace for the records; handles L <= 8 agents per scene
- *                      and B*L <= 1024 (larger shapes run HMVIT_ATTN_SINGLE).
+ *   HMVIT_ATTN_FUSED   default: a key-record pass once per forward (fp64 source-pixel maps, bit-exact ROI visibility,
+ *                      compaction of the visible keys; csrc/attn_fused.cuh tap_records_kernel) + ONE persistent
+ *                      warp-specialised tcgen05 kernel per stage (csrc/attn_fa2.cuh fused_attn2_kernel): gather warps
+ *                      blend the projected K' / V' taps straight into shared-memory operand tiles; S, P, D, Q and the
+ *                      softmax denominator live in tensor memory; the relative position bias is part of the Q K^T
+ *                      contraction.  Needs a workspace for the records; handles L <= 8 agents per scene and
+ *                      B*L <= 1024 (larger shapes run HMVIT_ATTN_SINGLE).
  *   HMVIT_ATTN_SPLIT   round-1 form, kept as an independently written cross-check: warp + compaction pass writing dense
  *                      key / value tiles to the workspace, then an mma.sync dense attention pass (csrc/attn_split.cuh).
  *   HMVIT_ATTN_SINGLE  one mma.sync kernel per (ego, group, head group), gather inside (csrc/attn.cuh); no workspace,

@@ -303,6 +303,26 @@ def _fusion_case(B, L, H, W, record_len, seed, pseed=0, mode=None, **kw):
     return cfg, P, (x, T, md, rl, mask), y, net
 
 
+def check_fusion_repeatable():
+    """The whole forward is BIT-REPRODUCIBLE over repeated runs at the BASELINE map size (the fused attention is a
+    persistent pipeline of five warp roles over mbarriers: a protocol error shows up as rare differing rows, not as a
+    crash), and its fused attention agrees with the independently written mma.sync kernel at operand-rounding level
+    (same bf16 operands, different tiling: measured 1.8e-3 .. 2.1e-3, bar 4e-3)."""
+    cfg, P, net = _mk_module(0)
+    x, T, md, rl, mask = _scene(2, 5, 48, 176, [5, 4], 77)
+    inp = [t.to(DEV) for t in (x, T, md, rl, mask)]
+    with torch.no_grad():
+        y0 = net(*inp).clone()
+        n_diff = 0
+        for _ in range(8):
+            n_diff += int((net(*inp) != y0).sum())
+        net.hetero_fusion_block.attn_impl = "single"
+        y1 = net(*inp)
+    res = {"differing_elements_over_8_runs": n_diff, "fused_vs_single_rel_l2": rel_l2(y0.cpu(), y1.cpu())}
+    assert n_diff == 0 and res["fused_vs_single_rel_l2"] < 4e-3, res
+    return res
+
+
 def check_fusion_small():
     """Whole forward, small shape, against the fp32 oracle and the operand-rounded emulation."""
     cfg, P, inp, y, net = _fusion_case(2, 3, 16, 24, [3, 2], seed=5, tx=10, ty=5)
@@ -575,6 +595,7 @@ CHECKS = {
     "attention_golden": check_attention_golden,
     "fusion_small": check_fusion_small,
     "fusion_golden": check_fusion_golden,
+    "fusion_repeatable": check_fusion_repeatable,
     "logits_golden": check_logits_golden,
     "decoder_vs_oracle": check_decoder_vs_oracle,
     "decoder_logits_golden": check_decoder_logits_golden,
