@@ -56,7 +56,7 @@ def main():
                 if op == mn or op.startswith(mn + ".") or (mn == "MUFU.EX2" and op.startswith("MUFU.EX2")):
                     counts[cur][mn] += 1
     names = demangle(sorted(usage))
-    print("# Static SASS / resource summary of hm-vit_b200/libhmvit_b200.so (sm_100a, final build of round 1)\n")
+    print("# Static SASS / resource summary of hm-vit_b200/libhmvit_b200.so (sm_100a, final build of round 2)\n")
     print("`python tools/sass_summary.py` (cuobjdump -res-usage / -sass; no GPU).  UTCHMMA = `tcgen05.mma`, LDTM / STTM = "
           "`tcgen05.ld` / `tcgen05.st`, UTMALDG / UTMASTG = TMA tensor copies, UBLKCP = `cp.async.bulk`, SYNCS = mbarrier, "
           "HMMA = `mma.sync`, STL / LDL = local-memory (spill) traffic.\n")
