@@ -9,11 +9,12 @@ from .fusion import (HeteroAttention, HeteroFeedForward, HeteroFusion, HeteroFus
                      get_roi_and_cav_mask, regroup)
 from .decoder import HeteroDecoder, NaiveDecoder  # noqa: F401
 from .model import BevformerPointPillarHetero, combine_features, unpad_features, unpad_mode_encoding  # noqa: F401
+from .postprocess import VoxelPostprocessor  # noqa: F401
 from .build import build_extension  # noqa: F401
 from .sharding import max_over_ranks, scene_shard  # noqa: F401
 from .distributed import FlatGradAllReduce  # noqa: F401
 
 __all__ = ["HeteroFusion", "HeteroFusionBlock", "HeteroAttention", "HeteroLayerNorm", "HeteroFeedForward",
            "HeteroPreNormResidual", "SpatialTransformation", "get_roi_and_cav_mask", "regroup",
-           "HeteroDecoder", "NaiveDecoder", "BevformerPointPillarHetero", "combine_features", "unpad_features",
+           "HeteroDecoder", "NaiveDecoder", "VoxelPostprocessor", "BevformerPointPillarHetero", "combine_features", "unpad_features",
            "unpad_mode_encoding", "build_extension", "ops", "training", "FlatGradAllReduce"]

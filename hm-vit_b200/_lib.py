@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("HMVIT_LIB", os.path.join(_HERE, "libhmvit_b200.so")) 
 GEMM_QKV, GEMM_OUT, GEMM_FFN1, GEMM_FFN2, GEMM_HEAD1, GEMM_HEAD2, GEMM_QKV_NOLN = range(7)
 GEMM_LN_LIN_CM, GEMM_LIN_CM, GEMM_LIN_ROWS, GEMM_ROWS_LIN_CM = range(7, 11)
 ATTN_FUSED, ATTN_SPLIT, ATTN_SINGLE = range(3)     # HmvitAttnArgs.impl
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 EXPORTS = (
     "hmvit_abi_version", "hmvit_last_error", "hmvit_rowgemm", "hmvit_group_attn", "hmvit_warp_bilinear",
@@ -20,7 +20,7 @@ EXPORTS = (
     "hmvit_out_ffn_chain", "hmvit_ffn_head",
     "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
     "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes", "hmvit_dropout", "hmvit_attn_records",
-    "hmvit_decoder_workspace_bytes", "hmvit_decoder_forward",
+    "hmvit_decoder_workspace_bytes", "hmvit_decoder_forward", "hmvit_postprocess_workspace_bytes", "hmvit_postprocess",
 )
 
 
@@ -77,6 +77,14 @@ class DecoderArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("num_convs", C.c_int32), ("anchor_number", C.c_int32),
                 ("ego_mode", C.c_void_p), ("x", C.c_void_p), ("conv_w", C.c_void_p), ("conv_b", C.c_void_p),
                 ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("psm", C.c_void_p), ("rm", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class PostArgs(C.Structure):
+    _fields_ = [("H", C.c_int32), ("W", C.c_int32), ("A", C.c_int32), ("psm", C.c_void_p), ("rm", C.c_void_p),
+                ("anchor_box", C.c_void_p), ("transformation_matrix", C.c_void_p), ("order_hwl", C.c_int32),
+                ("score_threshold", C.c_float), ("nms_thresh", C.c_float), ("range", C.c_float * 4),
+                ("out_boxes", C.c_void_p), ("out_scores", C.c_void_p), ("out_count", C.c_void_p), ("status", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
@@ -152,6 +160,10 @@ def load():
     lib.hmvit_decoder_workspace_bytes.restype = C.c_size_t
     lib.hmvit_decoder_forward.argtypes = [C.POINTER(DecoderArgs), vp]
     lib.hmvit_decoder_forward.restype = C.c_int
+    lib.hmvit_postprocess_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.hmvit_postprocess_workspace_bytes.restype = C.c_size_t
+    lib.hmvit_postprocess.argtypes = [C.POINTER(PostArgs), vp]
+    lib.hmvit_postprocess.restype = C.c_int
     for fn in ("hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
                "hmvit_bwd_wgrad", "hmvit_group_attn_bwd"):
         getattr(lib, fn).restype = C.c_int

@@ -12,6 +12,7 @@
 #include "chain.cuh"
 #include "qkv.cuh"
 #include "decoder.cuh"
+#include "postproc.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -833,6 +834,55 @@ extern "C" int hmvit_decoder_forward(const HmvitDecoderArgs* a, void* stream) {
   hp.B = a->B; hp.N = N; hp.n_cls = a->anchor_number; hp.n_reg = 7 * a->anchor_number; hp.ego_mode = a->ego_mode;
   hp.x = act[a->num_convs & 1]; hp.w = a->head_w; hp.bias = a->head_b; hp.psm = a->psm; hp.rm = a->rm;
   det_heads_kernel<<<dim3((N + 127) / 128, a->B), 128, 0, st>>>(hp);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// detection post-processing (csrc/postproc.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t hmvit_postprocess_workspace_bytes(int32_t H, int32_t W, int32_t A) {
+  if (H <= 0 || W <= 0 || A <= 0) return 0;
+  const size_t n = static_cast<size_t>(H) * W * A;
+  return align_up(n, 256) + align_up(n * 4, 256) + align_up(n * 24 * 4, 256) + align_up(kPostMaxCand * 4, 256) +
+         align_up(kPostTop * 4, 256) + align_up(static_cast<size_t>(kPostTop) * kPostMaskWords * 8, 256) + 256;
+}
+extern "C" int hmvit_postprocess(const HmvitPostArgs* a, void* stream) {
+  HMVIT_CHECK_ARG(a != nullptr, "postprocess: null args");
+  HMVIT_CHECK_ARG(a->H > 0 && a->W > 0 && a->A > 0, "postprocess: bad shape");
+  HMVIT_CHECK_ARG(a->psm && a->rm && a->anchor_box && a->out_boxes && a->out_scores && a->out_count && a->status, "postprocess: null pointer");
+  HMVIT_CHECK_ARG(a->workspace != nullptr && a->workspace_bytes >= hmvit_postprocess_workspace_bytes(a->H, a->W, a->A), "postprocess: workspace too small");
+  HMVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(a->workspace) & 255) == 0, "postprocess: workspace must be 256-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(post_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPostMaxCand * 8);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  const size_t n = static_cast<size_t>(a->H) * a->W * a->A;
+  PostParams p;
+  p.H = a->H; p.W = a->W; p.A = a->A; p.psm = a->psm; p.rm = a->rm; p.anchors = a->anchor_box; p.tmat = a->transformation_matrix;
+  p.order_hwl = a->order_hwl ? 1 : 0; p.score_thr = a->score_threshold; p.nms_thr = a->nms_thresh;
+  for (int k = 0; k < 4; ++k) p.range[k] = a->range[k];
+  uint8_t* ws = static_cast<uint8_t*>(a->workspace);
+  p.keep = ws; ws += align_up(n, 256);
+  p.score = reinterpret_cast<float*>(ws); ws += align_up(n * 4, 256);
+  p.corners = reinterpret_cast<float*>(ws); ws += align_up(n * 24 * 4, 256);
+  p.cand = reinterpret_cast<int*>(ws); ws += align_up(kPostMaxCand * 4, 256);
+  p.order = reinterpret_cast<int*>(ws); ws += align_up(kPostTop * 4, 256);
+  p.mask = reinterpret_cast<unsigned long long*>(ws); ws += align_up(static_cast<size_t>(kPostTop) * kPostMaskWords * 8, 256);
+  p.n_cand = reinterpret_cast<int*>(ws); p.n_top = p.n_cand + 1;
+  p.out_boxes = a->out_boxes; p.out_scores = a->out_scores; p.out_count = a->out_count; p.status = a->status;
+  post_decode_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  post_compact_kernel<<<1, 1024, 0, st>>>(p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  post_sort_kernel<<<1, 1024, kPostMaxCand * 8, st>>>(p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  post_iou_kernel<<<dim3(kPostMaskWords, kPostTop), 64, 0, st>>>(p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  post_nms_kernel<<<1, 32, 0, st>>>(p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }

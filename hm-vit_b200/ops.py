@@ -273,3 +273,31 @@ def decoder_forward(*, x, ego_mode, conv_w, conv_b, head_w, head_b, anchor_numbe
     args.workspace, args.workspace_bytes = workspace.data_ptr(), workspace.numel()
     _lib.check(_lib.load().hmvit_decoder_forward(C.byref(args), _stream()))
     return psm, rm
+
+
+def postprocess(*, psm, rm, anchor_box, transformation_matrix, order_hwl, score_threshold, nms_thresh, gt_range):
+    """VoxelPostprocessor.post_process for one cav, batch 1 (include/hmvit_b200.h): returns device tensors
+    (boxes [1000][8][3], scores [1000], meta [3] int32 = (boxes kept, status, candidates before the NMS))."""
+    A, H, W = psm.shape[1], psm.shape[2], psm.shape[3]
+    dev = psm.device
+    lib = _lib.load()
+    nbytes = int(lib.hmvit_postprocess_workspace_bytes(H, W, A))
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 256
+    boxes = torch.empty(1000, 8, 3, dtype=torch.float32, device=dev)
+    scores = torch.empty(1000, dtype=torch.float32, device=dev)
+    meta = torch.zeros(3, dtype=torch.int32, device=dev)
+    args = _lib.PostArgs()
+    args.H, args.W, args.A = H, W, A
+    args.psm, args.rm, args.anchor_box = psm.data_ptr(), rm.data_ptr(), anchor_box.data_ptr()
+    args.transformation_matrix = transformation_matrix.data_ptr() if transformation_matrix is not None else None
+    args.order_hwl = 1 if order_hwl else 0
+    args.score_threshold, args.nms_thresh = float(score_threshold), float(nms_thresh)
+    args.range[0], args.range[1], args.range[2], args.range[3] = gt_range[0], gt_range[1], gt_range[3], gt_range[4]
+    args.out_boxes, args.out_scores = boxes.data_ptr(), scores.data_ptr()
+    args.out_count, args.status = meta[0:1].data_ptr(), meta[1:2].data_ptr()
+    args.workspace, args.workspace_bytes = ws.data_ptr() + off, nbytes
+    _lib.check(lib.hmvit_postprocess(C.byref(args), _stream()))
+    # the candidate count lives in the last 256 bytes of the workspace (csrc/api.cu)
+    meta[2:3].copy_(ws[off + nbytes - 256: off + nbytes - 252].view(torch.int32))
+    return boxes, scores, meta

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMVIT_ABI_VERSION 6
+#define HMVIT_ABI_VERSION 7
 
 /* error codes */
 #define HMVIT_OK 0
@@ -342,6 +342,30 @@ typedef struct {
 } HmvitDecoderArgs;
 size_t hmvit_decoder_workspace_bytes(int32_t B, int32_t H, int32_t W);
 int hmvit_decoder_forward(const HmvitDecoderArgs* args, void* stream);
+
+/* ---- detection post-processing ----------------------------------------------------
+ * Replaces VoxelPostprocessor.post_process for the intermediate-fusion case (one 'ego' output, batch size 1)
+ *   opencood/data_utils/post_processor/voxel_postprocessor.py:232-343, 345-397 (delta_to_boxes3d)
+ *   opencood/utils/box_utils.py:139-184, 258-296, 326-357, 575-620 (nms_rotated), 722-772
+ * score threshold -> anchor decoding -> 8 corners -> projection -> sanity filters -> rotated NMS over the 1000 best-scored
+ * candidates (IoU of the quadrilaterals spanned by corners 0..3, fp64) -> range mask.  Kernels: csrc/postproc.cuh.
+ * Outputs stay on the device: out_boxes [1000][8][3], out_scores [1000], out_count [1] (boxes in the order the greedy NMS
+ * picked them, i.e. by descending score), status [1] = 1 if more than 16384 anchors passed the threshold and filters. */
+typedef struct {
+  int32_t H, W, A;            /* feature map of psm / rm, anchors per cell */
+  const float* psm;           /* fp32 (1, A, H, W) */
+  const float* rm;            /* fp32 (1, 7 A, H, W) */
+  const float* anchor_box;    /* fp32 (H, W, A, 7): x, y, z, h, w, l, r ('hwl') */
+  const float* transformation_matrix;   /* fp32 4x4 row-major, or NULL ('no_post_projection') */
+  int32_t order_hwl;          /* 1: params['order'] == 'hwl', 0: 'lwh' */
+  float score_threshold, nms_thresh;
+  float range[4];             /* GT_RANGE x_min, y_min, x_max, y_max */
+  float* out_boxes; float* out_scores; int32_t* out_count; int32_t* status;
+  void* workspace;            /* hmvit_postprocess_workspace_bytes(H, W, A), 256-byte aligned */
+  size_t workspace_bytes;
+} HmvitPostArgs;
+size_t hmvit_postprocess_workspace_bytes(int32_t H, int32_t W, int32_t A);
+int hmvit_postprocess(const HmvitPostArgs* args, void* stream);
 
 #ifdef __cplusplus
 }

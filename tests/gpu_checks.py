@@ -468,6 +468,37 @@ def check_model_glue():
     return res
 
 
+def check_postprocess_golden():
+    """Detection post-processing on the GPU (hmvit_postprocess: threshold, anchor decoding, corners, projection, filters,
+    rotated NMS, range mask) against the outputs of the UNMODIFIED reference post-processor (tests/golden/postproc.npz;
+    shapely's polygon areas replaced by the oracle's convex clipping there: that part is parity-unpinned).  Bar: the SAME
+    boxes in the SAME order (count and score order), corners within 1e-4 m, scores within 1e-6."""
+    sys.path.insert(0, GOLDEN)
+    import make_golden_postproc as G
+    g = np.load(os.path.join(GOLDEN, "postproc.npz"))
+    res = {}
+    for name, (H, W, seed, density) in G.CASES.items():
+        P = G.params(H, W)
+        pp = pkg().VoxelPostprocessor(P, train=False)
+        anchors = pp.generate_anchor_box()
+        psm, rm = G.synth_outputs(H, W, 2, seed, density)
+        T = torch.from_numpy(g[f"{name}_T"])
+        for tag in ("proj", "noproj"):
+            cav = {"transformation_matrix": T, "anchor_box": torch.from_numpy(anchors)}
+            if tag == "noproj":
+                cav["no_post_projection"] = True
+            boxes, scores = pp.post_process({"ego": cav}, {"ego": {"psm": psm.to(DEV), "rm": rm.to(DEV)}})
+            rb, rs = torch.from_numpy(g[f"{name}_{tag}_boxes"]), torch.from_numpy(g[f"{name}_{tag}_scores"])
+            assert tuple(boxes.shape) == tuple(rb.shape), (name, tag, tuple(boxes.shape), tuple(rb.shape))
+            db, ds = float((boxes.cpu() - rb).abs().max()), float((scores.cpu() - rs).abs().max())
+            res[f"{name}_{tag}"] = {"boxes": int(rb.shape[0]), "max_abs_corner_diff": db, "max_abs_score_diff": ds}
+            assert db < 1e-4 and ds < 1e-6, res
+    # nothing above the threshold: (None, None) like the reference (:313-314)
+    none = pp.post_process({"ego": cav}, {"ego": {"psm": torch.full((1, 2, 48, 176), -9.0, device=DEV), "rm": rm.to(DEV)}})
+    assert none == (None, None)
+    return res
+
+
 def check_fusion_config5_scene():
     """BASELINE config 5 shape, one scene: 7 agents (LiDAR ego + 6 camera collaborators), 256x96x352."""
     cfg, P, inp, y, net = _fusion_case(1, 7, 96, 352, [7], seed=1239, mode=[[1, 0, 0, 0, 0, 0, 0]], tx=100.0, ty=30.0)
@@ -600,6 +631,7 @@ CHECKS = {
     "decoder_vs_oracle": check_decoder_vs_oracle,
     "decoder_logits_golden": check_decoder_logits_golden,
     "model_glue": check_model_glue,
+    "postprocess_golden": check_postprocess_golden,
     "fusion_config1": check_fusion_config1,
     "fusion_config2_scene": check_fusion_config2_scene,
     "fusion_properties": check_fusion_properties,
