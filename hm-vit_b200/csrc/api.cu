@@ -788,7 +788,7 @@ static int make_act_tmap(CUtensorMap* map, const void* act, int B, int H, int W)
   if (!g_encode) return fail(HMVIT_ERR_CUDA, "hmvit: cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {256, static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
   cuuint64_t strides[3] = {512, static_cast<cuuint64_t>(W) * 512, static_cast<cuuint64_t>(H) * W * 512};
-  cuuint32_t box[4] = {64, DecCfg::TW, DecCfg::TH, 1};
+  cuuint32_t box[4] = {64, DecCfg::TW, DecCfg::BOX_H, 1};   // one half tile per load
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(act), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -6,13 +6,15 @@
 // the two 1x1 heads.  BatchNorm is folded into the convolution on the host (hm-vit_b200/decoder.py).
 //
 //   nchw_to_nhwc_f16_kernel   fused feature fp32 (B,256,H,W) -> fp16 pixel rows [B][H][W][256] (what the TMA boxes want)
-//   conv3x3_kernel            TMA-shifted implicit GEMM on tcgen05: one CTA = 8 x 16 output pixels x 256 output channels.
+//   conv3x3_kernel            TMA-shifted implicit GEMM on tcgen05: one CTA = 16 x 16 output pixels (two M = 128 halves that share
+//                             every weight block: the kernel is bound by the L2 -> shared-memory stream, 48 KB per 512 MMA
+//                             cycles with one half, 64 KB per 1024 with two) x 256 output channels.
 //                             The 3x3 taps are nine K-blocks of the same GEMM: for tap (dy, dx) the A tile is ONE 4-D TMA box
 //                             [1 scene][8 rows][16 cols][64 channels] loaded at pixel offset (dy, dx) -- rows outside the
 //                             map arrive as zeros (TMA out-of-bounds fill), which is the convolution's zero padding -- and
 //                             the B tile the tap's [256 out][64 in] weight block of the ego's modality.  36 K-blocks of 64
-//                             through a 4-stage ring, accumulator 128 x 256 fp32 in tensor memory, epilogue + bias, ReLU,
-//                             fp16 pixel rows.  fp16 operands (11-bit significand, like the FFN of the fusion block): bf16
+//                             through a 3-stage 64 KB ring, two 128 x 256 fp32 accumulators (all 512 columns of tensor
+//                             memory), epilogue + bias, ReLU, fp16 pixel rows.  fp16 operands (11-bit significand, like the FFN of the fusion block): bf16
 //                             would put ~3e-3 per layer on the logits, the stated tolerance is 1e-3.
 //   det_heads_kernel          the 1x1 classification / regression heads on the last feature: fp32, thread == pixel.
 #pragma once
@@ -23,16 +25,17 @@
 namespace hmvit {
 
 struct DecCfg {
-  static constexpr int TH = 8, TW = 16;                 // output tile: 8 rows x 16 columns = 128 pixels
-  static constexpr int STAGES = 4;
-  static constexpr int A_BYTES = 128 * 128;             // 128 pixels x 64 channels fp16
+  static constexpr int TH = 16, TW = 16;                // output tile: 2 halves of 8 rows x 16 columns = 2 x 128 pixels
+  static constexpr int BOX_H = 8;                       // rows of one TMA activation box (one M = 128 half)
+  static constexpr int STAGES = 3;
+  static constexpr int A_BYTES = 128 * 128;             // one half: 128 pixels x 64 channels fp16
   static constexpr int B_BYTES = 256 * 128;             // 256 output channels x 64 input channels fp16
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + B_BYTES; // 64 KB
   static constexpr int KBLOCKS = 9 * 4;                 // 9 taps x 4 channel blocks of 64
   static constexpr int OFF_BAR = STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int THREADS = 192;                   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-  static constexpr uint32_t TM_COLS = 256;
+  static constexpr uint32_t TM_COLS = 512;              // two 128 x 256 fp32 accumulators
 };
 
 struct ConvParams {
@@ -92,7 +95,8 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
         uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
         mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
         tma_load_4d(sa, &tmap_x, &full[s], cb * 64, w0 + dx, h0 + dy, b);
-        tma_load_2d(sa + Cfg::A_BYTES, &tmap_w, &full[s], cb * 64, (type * 9 + tap) * 256);
+        tma_load_4d(sa + Cfg::A_BYTES, &tmap_x, &full[s], cb * 64, w0 + dx, h0 + 8 + dy, b);
+        tma_load_2d(sa + 2 * Cfg::A_BYTES, &tmap_w, &full[s], cb * 64, (type * 9 + tap) * 256);
       }
       __syncwarp();
     }
@@ -104,10 +108,13 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
       mbar_wait(&full[s], (kb / Cfg::STAGES) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES), sb = sa + Cfg::A_BYTES;
+        const uint32_t sa = smem_u32(smem + s * Cfg::STAGE_BYTES), sb = sa + 2 * Cfg::A_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ss<2>(tm, umma_desc_sw128(sa + ks * 32), umma_desc_sw128(sb + ks * 32), idesc, (kb | ks) != 0 ? 1u : 0u);
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_ss<2>(tm + hf * 256, umma_desc_sw128(sa + hf * Cfg::A_BYTES + ks * 32), umma_desc_sw128(sb + ks * 32), idesc,
+                       (kb | ks) != 0 ? 1u : 0u);
         umma_commit(&empty[s]);
         if (kb == Cfg::KBLOCKS - 1) umma_commit(acc_full);
       }
@@ -116,16 +123,17 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
   } else {
     // ------------------------------ epilogue: + bias, ReLU, fp16 pixel rows ------------------------------
     const int q = warp & 3;                                         // TMEM lane quadrant this warp may read
-    const int pix = q * 32 + lane;                                  // pixel of the tile == accumulator row
-    const int h = h0 + (pix >> 4), w = w0 + (pix & 15);
-    const bool inside = h < p.H && w < p.W;
+    const int pix = q * 32 + lane;                                  // pixel of a half tile == accumulator row
     const float* bias = p.bias + type * 256;
-    __half* orow = p.out + ((static_cast<size_t>(b) * p.H + h) * p.W + w) * 256;
     mbar_wait_sleepy(acc_full, 0);
     tc_fence_after();
-    const uint32_t taddr = tm + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
+    for (int c16 = 0; c16 < 16; ++c16) {
+      const int hf = c16 >> 3, c = c16 & 7;
+      const int h = h0 + hf * 8 + (pix >> 4), w = w0 + (pix & 15);
+      const bool inside = h < p.H && w < p.W;
+      __half* orow = p.out + ((static_cast<size_t>(b) * p.H + (inside ? h : 0)) * p.W + (inside ? w : 0)) * 256;
+      const uint32_t taddr = tm + hf * 256 + (static_cast<uint32_t>(q * 32) << 16);
       uint32_t v[32];
       tmem_ld32(taddr + c * 32, v);
       tmem_ld_wait();
