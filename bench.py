@@ -270,6 +270,89 @@ def stress_variant(pkg, net, dev, steps=3, warmup=1):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def config3_variant(pkg, dev, scenes=2, steps=3, warmup=2):
+    """BASELINE configs[2]: the full inference path of one GPU's shard -- 4 x 512 x 512 camera images per camera agent through
+    the CVT camera branch (ResNet-34 + two cross-view attention levels) and ~6000 pillars per LiDAR agent through PointPillar
+    (704 x 192 grid), then combine / regroup -> HeteroFusion -> HeteroDecoder -> psm / rm, through
+    `BevformerPointPillarHetero.forward(batch)` (hm-vit_b200/encoders.py::build_config3_model).  The encoders are torch / cuDNN
+    library modules at torch's default precision (SURVEY 8 f-3 "library-backed first"); random-init weights, synthetic
+    OPV2V-shaped inputs drawn on the device, 5 agents per scene alternating LiDAR / camera with a LiDAR ego.  A reported side
+    figure with its split (CUDA events): encoders vs fusion + decoder."""
+    try:
+        from oracle import hmvit_oracle as O
+        enc = pkg.encoders
+        args = enc.config3_args()
+        torch.manual_seed(0)
+        net = enc.build_config3_model(args).eval().to(dev)
+        Lc = 5
+        mode = torch.tensor([[(a + 1 + b) % 2 for a in range(Lc)] for b in range(scenes)])        # 1 = LiDAR; egos alternate
+        rl = torch.full((scenes,), Lc, dtype=torch.long)
+        _, T, _, _, _ = O.synth_inputs(scenes, Lc, 1, H, W, [Lc] * scenes, 1234 + 3)
+        n_agents = scenes * Lc
+        g = torch.Generator(device=dev).manual_seed(1234 + 3)
+        la = args['lidar']
+        nx, ny, _ = la['point_pillar_scatter']['grid_size']
+        per_agent, pts = 6000, 32
+        feats, coords, nums = [], [], []
+        for a in range(n_agents):
+            cell = torch.randperm(nx * ny, device=dev, generator=g)[:per_agent]
+            cy, cx = cell // nx, cell % nx
+            npt = torch.randint(1, pts + 1, (per_agent,), device=dev, generator=g)
+            u = torch.rand(per_agent, pts, 4, device=dev, generator=g)
+            p = torch.stack([la['lidar_range'][0] + (cx[:, None] + u[..., 0]) * la['voxel_size'][0],
+                             la['lidar_range'][1] + (cy[:, None] + u[..., 1]) * la['voxel_size'][1],
+                             la['lidar_range'][2] + u[..., 2] * la['voxel_size'][2], u[..., 3]], dim=-1)
+            feats.append(p * (torch.arange(pts, device=dev)[None, :] < npt[:, None])[..., None])
+            coords.append(torch.stack([torch.full_like(cx, a), torch.zeros_like(cx), cy, cx], dim=1))
+            nums.append(npt)
+        image = args['camera']['encoder']['image_height']
+        K = torch.eye(3, device=dev).repeat(n_agents, 4, 1, 1)
+        K[..., 0, 0] = K[..., 1, 1] = float(image)
+        K[..., 0, 2] = K[..., 1, 2] = image / 2
+        E = torch.eye(4, device=dev).repeat(n_agents, 4, 1, 1)
+        E[..., :3, 3] = torch.randn(n_agents, 4, 3, device=dev, generator=g)
+        batch = {'mode': mode.to(dev), 'record_len': rl.to(dev), 'pairwise_t_matrix': T.to(dev),
+                 'processed_lidar': {'voxel_features': torch.cat(feats), 'voxel_coords': torch.cat(coords).int(),
+                                     'voxel_num_points': torch.cat(nums).int()},
+                 'camera': torch.rand(n_agents, 4, image, image, 3, device=dev, generator=g), 'intrinsic': K, 'extrinsic': E,
+                 'cav2cam_extrinsic': E}
+        M = sys.modules["hmvit_b200.model"]
+        mu = M.unpad_mode_encoding(batch['mode'].to(torch.int), batch['record_len'])
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        torch.cuda.reset_peak_memory_stats(dev)
+        with torch.no_grad():
+            for _ in range(warmup):
+                out = net(batch)
+            torch.cuda.synchronize()
+            ev[0].record()
+            for _ in range(steps):
+                out = net(batch)
+            ev[1].record()
+            torch.cuda.synchronize()
+            # split: the two encoders alone on the same inputs
+            ev[2].record()
+            for _ in range(steps):
+                cf = net.camera_encoder(net.extract_camera_input(batch, mu))
+                lf = net.lidar_encoder(net.extract_lidar_input(batch, mu))
+            ev[3].record()
+            torch.cuda.synchronize()
+        ms, ms_enc = ev[0].elapsed_time(ev[1]) / steps, ev[2].elapsed_time(ev[3]) / steps
+        res = {"workload": f"BASELINE config 3: {scenes} scenes x 5 agents (LiDAR / camera alternating), 4 x 512 x 512 images per camera "
+                           f"agent (ResNet-34 + CVT, dim 256), {per_agent} pillars per LiDAR agent (PointPillar 704 x 192), fusion + decoder "
+                           "at 256x48x176, one GPU",
+               "ms_per_step": ms, "scenes_per_s": scenes / (ms * 1e-3), "steps": steps, "warmup": warmup,
+               "encoders_ms_per_step": ms_enc, "fusion_decoder_glue_ms_per_step": ms - ms_enc,
+               "camera_agents": int((mu == 0).sum()), "lidar_agents": int((mu == 1).sum()),
+               "finite": bool(torch.isfinite(out['psm']).all() and torch.isfinite(out['rm']).all()),
+               "peak_mem_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),
+               "note": "encoders = torch / cuDNN library modules (not hand-written kernels), default torch precision (cuDNN TF32 convs)"}
+        del net, batch, out, cf, lf
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:      # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 # ---------------------------------------------------------------------------------------------
 def kernel_breakdown(pkg, net, inp, iters=3):
     """Per-kernel CUDA-event times of one forward, issued op by op through the same C-ABI entry points
@@ -515,9 +598,10 @@ def main():
         kern = kernel_breakdown(pkg, net, dev_in) if rank == 0 else None
         ragged = ragged_variant(net, dev, Bq, args.steps, args.warmup) if rank == 0 and world == 1 else None
         detector = detector_variant(pkg, net, dev, dev_in, args.steps, args.warmup) if rank == 0 and world == 1 else None
-    stress = None
+    stress = config3 = None
     if not args.no_stress and rank == 0 and world == 1:
         stress = stress_variant(pkg, net, dev)
+        config3 = config3_variant(pkg, dev)
     train = train_drop = None
     if not args.no_train:
         train = train_step_bench(pkg, dev, dist, world, rank, Bq, steps=max(2, min(args.steps, 5)))
@@ -619,6 +703,8 @@ def main():
         line["train_step_dropout"] = train_drop
     if stress is not None:
         line["stress_variant"] = stress
+    if config3 is not None:
+        line["config3_variant"] = config3
     if ragged is not None:
         line["ragged_variant"] = ragged
     if detector is not None:

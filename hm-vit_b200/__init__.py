@@ -10,6 +10,8 @@ from .fusion import (HeteroAttention, HeteroFeedForward, HeteroFusion, HeteroFus
 from .decoder import HeteroDecoder, NaiveDecoder  # noqa: F401
 from .model import BevformerPointPillarHetero, combine_features, unpad_features, unpad_mode_encoding  # noqa: F401
 from .postprocess import VoxelPostprocessor  # noqa: F401
+from . import encoders  # noqa: F401
+from .encoders import CvtCameraEncoder, PointPillar, build_config3_model, config3_args  # noqa: F401
 from .build import build_extension  # noqa: F401
 from .sharding import max_over_ranks, scene_shard  # noqa: F401
 from .distributed import FlatGradAllReduce  # noqa: F401
@@ -17,4 +19,4 @@ from .distributed import FlatGradAllReduce  # noqa: F401
 __all__ = ["HeteroFusion", "HeteroFusionBlock", "HeteroAttention", "HeteroLayerNorm", "HeteroFeedForward",
            "HeteroPreNormResidual", "SpatialTransformation", "get_roi_and_cav_mask", "regroup",
            "HeteroDecoder", "NaiveDecoder", "VoxelPostprocessor", "BevformerPointPillarHetero", "combine_features", "unpad_features",
-           "unpad_mode_encoding", "build_extension", "ops", "training", "FlatGradAllReduce"]
+           "unpad_mode_encoding", "encoders", "PointPillar", "CvtCameraEncoder", "build_config3_model", "config3_args", "build_extension", "ops", "training", "FlatGradAllReduce"]

@@ -6,9 +6,10 @@
 i.e. everything between the two BEV encoders and the output dict:
     per-agent camera / LiDAR BEV features -> combine (agent order) -> regroup (B, L, C, H, W) + mask -> HeteroFusion
     (hmvit_fusion_forward) -> HeteroDecoder (hmvit_decoder_forward) -> {'psm', 'rm'}.
-The encoders themselves (BEVFormer / CVT camera branch, PointPillar) are NOT rebuilt: they are passed in
-(`camera_encoder`, `lidar_encoder`: any modules mapping the reference's `extract_*_input(batch)` dicts to (n, 256, H, W)
-features), or the caller hands the features to `forward_features` directly.  `compression > 0` (NaiveCompressor) is not
+The encoders are passed in (`camera_encoder`, `lidar_encoder`: any modules mapping the reference's `extract_*_input(batch)`
+dicts to (n, 256, H, W) features -- `hm-vit_b200/encoders.py` has library-backed mirrors of PointPillar and the CVT camera branch
+and `build_config3_model`; the shipped yaml's BEVFormer / mmcv branch is not rebuilt), or the caller hands the
+features to `forward_features` directly.  `compression > 0` (NaiveCompressor) is not
 used by the shipped yaml (`hypes_yaml/opcl/bevformer_point_pillar_hetero.yaml:83`) and raises.
 """
 import torch
@@ -101,12 +102,12 @@ class BevformerPointPillarHetero(nn.Module):
         camera_features = lidar_features = None
         if not bool(torch.all(mode_unpack == 1)):
             if self.camera_encoder is None:
-                raise NotImplementedError("no camera encoder was passed in (SURVEY.md 8 f-3 is not rebuilt); "
+                raise NotImplementedError("no camera encoder was passed in (see hm-vit_b200/encoders.py::CvtCameraEncoder); "
                                           "call forward_features with precomputed BEV features")
             camera_features = self.camera_encoder(self.extract_camera_input(batch, mode_unpack))
         if not bool(torch.all(mode_unpack == 0)):
             if self.lidar_encoder is None:
-                raise NotImplementedError("no lidar encoder was passed in (SURVEY.md 8 f-3 is not rebuilt); "
+                raise NotImplementedError("no lidar encoder was passed in (see hm-vit_b200/encoders.py::PointPillar); "
                                           "call forward_features with precomputed BEV features")
             lidar_features = self.lidar_encoder(self.extract_lidar_input(batch, mode_unpack))
         return self.forward_features(camera_features, lidar_features, mode, record_len, batch['pairwise_t_matrix'])

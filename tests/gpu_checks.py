@@ -1279,3 +1279,82 @@ def check_fp16_feature_boundary():
 
 
 CHECKS.update({"fp16_feature_boundary": check_fp16_feature_boundary})
+
+
+# ------------------------------------------------------------------------------------------------
+# BEV encoders and BASELINE config 3
+# ------------------------------------------------------------------------------------------------
+def _config3_parts():
+    import enc_synth as S
+    sys.path.insert(0, GOLDEN)
+    import make_golden_encoders as G
+    enc = pkg().encoders
+    args = enc.config3_args(bev_h=G.BEV_H, bev_w=G.BEV_W, image=G.IMAGE)
+    la = args['lidar']
+    nx, ny, _ = la['point_pillar_scatter']['grid_size']
+    vox = S.synth_voxels(2, nx, ny, 400, la['lidar_range'], la['voxel_size'], seed=1)
+    cams = S.synth_cameras(3, 2, G.IMAGE, seed=2)
+    return S, G, enc, args, vox, cams, np.load(os.path.join(GOLDEN, "encoders.npz"))
+
+
+def check_encoders_golden():
+    """PointPillar and the CVT camera branch (library-backed torch modules, hm-vit_b200/encoders.py) ON THE GPU against the
+    outputs of the unmodified reference modules.  cuDNN / cuBLAS TF32 is switched off for the comparison (fp32 like the
+    reference on CPU); stated tolerance rel-L2 <= 1e-3 per tensor."""
+    S, G, enc, args, vox, cams, gold = _config3_parts()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        pp = enc.PointPillar(args['lidar']).eval()
+        pp.load_state_dict(S.synth_module_state_dict(pp, 1), strict=True)
+        pp = pp.to(DEV).set_return_features()
+        cam = enc.CvtCameraEncoder(args['camera']).eval()
+        cam.encoder.load_state_dict(S.synth_module_state_dict(cam.encoder, 2), strict=True)
+        cam.cvm.load_state_dict(S.synth_module_state_dict(cam.cvm, 3), strict=True)
+        cam = cam.to(DEV)
+        with torch.no_grad():
+            lf = pp({'processed_lidar': {k: v.to(DEV) for k, v in vox.items()}, 'batch_size': 2})
+            cf = cam({k: v.to(DEV) for k, v in cams.items()})
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    res = {"point_pillar_rel_l2": rel_l2(lf.cpu(), torch.from_numpy(gold['pp_features'])),
+           "cvt_rel_l2": rel_l2(cf.cpu(), torch.from_numpy(gold['cvt_features']))}
+    assert res["point_pillar_rel_l2"] < 1e-3 and res["cvt_rel_l2"] < 1e-3, res
+    return res
+
+
+def check_config3_golden():
+    """BASELINE config 3 end to end on the GPU: raw voxels + camera images -> encoders -> combine / regroup -> HeteroFusion
+    (hmvit_fusion_forward) -> HeteroDecoder (hmvit_decoder_forward) -> psm / rm through `BevformerPointPillarHetero.forward(batch)`,
+    against the same pipeline assembled from the UNMODIFIED reference modules (tests/golden/encoders.npz).  Stated tolerance
+    for this composed case: rel-L2 <= 2e-3 per tensor (see check_model_glue)."""
+    S, G, enc, args, vox, cams, gold = _config3_parts()
+    mode = torch.tensor(G.C3_MODE)
+    rl = torch.tensor(G.C3_RECORD_LEN)
+    cfgf = O.default_config()
+    args = dict(args, hetero_fusion=cfgf, spatial_transform=cfgf["spatial_transform"], max_cav=3)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        net = enc.build_config3_model(args).eval()
+        net.lidar_encoder.load_state_dict(S.synth_module_state_dict(net.lidar_encoder, 1), strict=True)
+        net.camera_encoder.encoder.load_state_dict(S.synth_module_state_dict(net.camera_encoder.encoder, 2), strict=True)
+        net.camera_encoder.cvm.load_state_dict(S.synth_module_state_dict(net.camera_encoder.cvm, 3), strict=True)
+        net.fusion_net.load_state_dict(O.synth_state_dict(cfgf, 0), strict=True)
+        net.decoder.load_state_dict(O.synth_decoder_state_dict(1), strict=True)
+        net = net.to(DEV)
+        batch = S.config3_batch(vox, cams, G.C3_ORDER, mode, rl, torch.from_numpy(gold['c3_T']))
+
+        def to_dev(v):
+            return {k: to_dev(x) for k, x in v.items()} if isinstance(v, dict) else v.to(DEV)
+        with torch.no_grad():
+            out = net(to_dev(batch))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    res = {"psm_rel_l2": rel_l2(out["psm"].cpu(), torch.from_numpy(gold['c3_psm'])),
+           "rm_rel_l2": rel_l2(out["rm"].cpu(), torch.from_numpy(gold['c3_rm']))}
+    assert res["psm_rel_l2"] < 2e-3 and res["rm_rel_l2"] < 2e-3, res
+    return res
+
+
+CHECKS.update({"encoders_golden": check_encoders_golden, "config3_golden": check_config3_golden})
