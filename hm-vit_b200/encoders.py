@@ -316,6 +316,31 @@ class CrossAttention(nn.Module):
         self.mlp = nn.Sequential(nn.Linear(dim, 2 * dim), nn.GELU(), nn.Linear(2 * dim, dim))
         self.postnorm = norm(dim)
         self.max_logits = 1 << 30              # elements of one logits tensor; agents are processed in chunks below this
+        self.fused = True                      # CUDA: per-camera fused attention (library kernel) + log-sum-exp merge
+
+    def _attend_exact(self, q, k, v):
+        """fp32 reference form: logits of all cameras of an agent materialised, one softmax over (camera, pixel)."""
+        b, n, Q, m, _ = q.shape
+        step = max(1, self.max_logits // max(1, m * Q * n * k.shape[2]))
+        outs = []
+        for s in range(0, b, step):
+            logits = self.scale * torch.einsum('bnqmd,bnkmd->bmqnk', q[s:s + step], k[s:s + step])
+            att = logits.flatten(3).softmax(dim=-1)                                        # over (camera, pixel)
+            outs.append(torch.einsum('bmqk,bkmd->bqmd', att, v[s:s + step].flatten(1, 2)).flatten(2))
+        return torch.cat(outs) if len(outs) > 1 else outs[0]
+
+    def _attend_fused(self, q, k, v):
+        """The same softmax without the (Q x n K) logits in HBM: one memory-efficient attention call per (agent, camera) that
+        also returns the log-sum-exp of its logits, then the cameras are merged with weights exp(lse_n - logsumexp_n lse_n).
+        Library kernel (torch's cutlass FMHA: TF32 tensor-core contractions for fp32 inputs)."""
+        b, n, Q, m, dh = q.shape
+
+        def bh(t):                                                                         # (b, n, L, m, d) -> (b n, m, L, d)
+            return t.permute(0, 1, 3, 2, 4).reshape(b * n, m, t.shape[2], dh).contiguous()
+        out, lse = torch.ops.aten._scaled_dot_product_efficient_attention(bh(q), bh(k), bh(v), None, True, scale=self.scale)[:2]
+        w = lse[..., :Q].reshape(b, n, m, Q).softmax(dim=1)                                # weight of a camera for (head, query)
+        out = (out.reshape(b, n, m, Q, dh) * w[..., None]).sum(dim=1)                      # (b, m, Q, d)
+        return out.transpose(1, 2).reshape(b, Q, m * dh)
 
     def forward(self, q, k, v, skip=None):
         """q (b, n, d, H, W), k / v (b, n, d, h, w) -> (b, d, H, W)."""
@@ -324,14 +349,8 @@ class CrossAttention(nn.Module):
         q = self.to_q(q.flatten(3).transpose(2, 3)).view(b, n, H * W, m, dh)
         k = self.to_k(k.flatten(3).transpose(2, 3)).view(b, n, -1, m, dh)
         v = self.to_v(v.flatten(3).transpose(2, 3)).view(b, n, -1, m, dh)
-        K = k.shape[2]
-        step = max(1, self.max_logits // max(1, m * H * W * n * K))
-        outs = []
-        for s in range(0, b, step):
-            logits = self.scale * torch.einsum('bnqmd,bnkmd->bmqnk', q[s:s + step], k[s:s + step])
-            att = logits.flatten(3).softmax(dim=-1)                                        # over (camera, pixel)
-            outs.append(torch.einsum('bmqk,bkmd->bqmd', att, v[s:s + step].flatten(1, 2)).flatten(2))
-        z = self.proj(torch.cat(outs) if len(outs) > 1 else outs[0])
+        a = self._attend_fused(q, k, v) if (self.fused and q.is_cuda and not torch.is_grad_enabled()) else self._attend_exact(q, k, v)
+        z = self.proj(a)
         if skip is not None:
             z = z + skip.flatten(2).transpose(1, 2)
         z = self.prenorm(z)

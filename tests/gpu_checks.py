@@ -1314,12 +1314,17 @@ def check_encoders_golden():
         cam = cam.to(DEV)
         with torch.no_grad():
             lf = pp({'processed_lidar': {k: v.to(DEV) for k, v in vox.items()}, 'batch_size': 2})
-            cf = cam({k: v.to(DEV) for k, v in cams.items()})
+            cams_d = {k: v.to(DEV) for k, v in cams.items()}
+            cf_fused = cam(cams_d)                      # default on CUDA: per-camera fused attention + log-sum-exp merge
+            for cv in cam.cvm.cross_views:
+                cv.cross_attend.fused = False
+            cf = cam(cams_d)                            # materialised fp32 logits, the reference's form
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     res = {"point_pillar_rel_l2": rel_l2(lf.cpu(), torch.from_numpy(gold['pp_features'])),
-           "cvt_rel_l2": rel_l2(cf.cpu(), torch.from_numpy(gold['cvt_features']))}
-    assert res["point_pillar_rel_l2"] < 1e-3 and res["cvt_rel_l2"] < 1e-3, res
+           "cvt_rel_l2": rel_l2(cf.cpu(), torch.from_numpy(gold['cvt_features'])),
+           "cvt_fused_attention_rel_l2": rel_l2(cf_fused.cpu(), torch.from_numpy(gold['cvt_features']))}
+    assert res["point_pillar_rel_l2"] < 1e-3 and res["cvt_rel_l2"] < 1e-3 and res["cvt_fused_attention_rel_l2"] < 1e-3, res
     return res
 
 
