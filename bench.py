@@ -277,7 +277,7 @@ def config3_variant(pkg, dev, scenes=2, steps=3, warmup=2):
     `BevformerPointPillarHetero.forward(batch)` (hm-vit_b200/encoders.py::build_config3_model).  The encoders are torch / cuDNN
     library modules at torch's default precision (SURVEY 8 f-3 "library-backed first"); random-init weights, synthetic
     OPV2V-shaped inputs drawn on the device, 5 agents per scene alternating LiDAR / camera with a LiDAR ego.  A reported side
-    figure with its split (CUDA events): encoders vs fusion + decoder."""
+    figure with its split (CUDA events, each part timed alone on the same inputs): encoders, fusion + decoder + glue."""
     try:
         from oracle import hmvit_oracle as O
         enc = pkg.encoders
@@ -318,7 +318,7 @@ def config3_variant(pkg, dev, scenes=2, steps=3, warmup=2):
                  'cav2cam_extrinsic': E}
         M = sys.modules["hmvit_b200.model"]
         mu = M.unpad_mode_encoding(batch['mode'].to(torch.int), batch['record_len'])
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         torch.cuda.reset_peak_memory_stats(dev)
         with torch.no_grad():
             for _ in range(warmup):
@@ -329,19 +329,22 @@ def config3_variant(pkg, dev, scenes=2, steps=3, warmup=2):
                 out = net(batch)
             ev[1].record()
             torch.cuda.synchronize()
-            # split: the two encoders alone on the same inputs
+            # split: the two encoders alone, then everything behind them alone, on the same inputs
             ev[2].record()
             for _ in range(steps):
                 cf = net.camera_encoder(net.extract_camera_input(batch, mu))
                 lf = net.lidar_encoder(net.extract_lidar_input(batch, mu))
             ev[3].record()
+            for _ in range(steps):
+                net.forward_features(cf, lf, batch['mode'], batch['record_len'], batch['pairwise_t_matrix'])
+            ev[4].record()
             torch.cuda.synchronize()
-        ms, ms_enc = ev[0].elapsed_time(ev[1]) / steps, ev[2].elapsed_time(ev[3]) / steps
+        ms, ms_enc, ms_rest = ev[0].elapsed_time(ev[1]) / steps, ev[2].elapsed_time(ev[3]) / steps, ev[3].elapsed_time(ev[4]) / steps
         res = {"workload": f"BASELINE config 3: {scenes} scenes x 5 agents (LiDAR / camera alternating), 4 x 512 x 512 images per camera "
                            f"agent (ResNet-34 + CVT, dim 256), {per_agent} pillars per LiDAR agent (PointPillar 704 x 192), fusion + decoder "
                            "at 256x48x176, one GPU",
                "ms_per_step": ms, "scenes_per_s": scenes / (ms * 1e-3), "steps": steps, "warmup": warmup,
-               "encoders_ms_per_step": ms_enc, "fusion_decoder_glue_ms_per_step": ms - ms_enc,
+               "encoders_ms_per_step": ms_enc, "fusion_decoder_glue_ms_per_step": ms_rest,
                "camera_agents": int((mu == 0).sum()), "lidar_agents": int((mu == 1).sum()),
                "finite": bool(torch.isfinite(out['psm']).all() and torch.isfinite(out['rm']).all()),
                "peak_mem_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1),
