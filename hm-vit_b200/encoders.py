@@ -19,8 +19,7 @@ branch + PointPillar + fusion + detection decoder) behind `BevformerPointPillarH
 one model (its HM-ViT camera branch is BEVFormer on mmcv; `CrossViewTransformer.forward` calls an undefined `seg_head`,
 cross_view_transformer.py:48).
 """
-import math
-from typing import Dict, List, Sequence
+from typing import Dict
 
 import torch
 import torch.nn as nn
