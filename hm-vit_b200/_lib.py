@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("HMVIT_LIB", os.path.join(_HERE, "libhmvit_b200.so")) 
 GEMM_QKV, GEMM_OUT, GEMM_FFN1, GEMM_FFN2, GEMM_HEAD1, GEMM_HEAD2, GEMM_QKV_NOLN = range(7)
 GEMM_LN_LIN_CM, GEMM_LIN_CM, GEMM_LIN_ROWS, GEMM_ROWS_LIN_CM = range(7, 11)
 ATTN_FUSED, ATTN_SPLIT, ATTN_SINGLE = range(3)     # HmvitAttnArgs.impl
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 EXPORTS = (
     "hmvit_abi_version", "hmvit_last_error", "hmvit_rowgemm", "hmvit_group_attn", "hmvit_warp_bilinear",
@@ -20,7 +20,7 @@ EXPORTS = (
     "hmvit_out_ffn_chain", "hmvit_ffn_head",
     "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
     "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes", "hmvit_dropout", "hmvit_attn_records",
-    "hmvit_decoder_workspace_bytes", "hmvit_decoder_forward", "hmvit_postprocess_workspace_bytes", "hmvit_postprocess",
+    "hmvit_decoder_workspace_bytes", "hmvit_decoder_forward", "hmvit_postprocess_workspace_bytes", "hmvit_postprocess", "hmvit_pillar_scatter",
 )
 
 
@@ -86,6 +86,13 @@ class PostArgs(C.Structure):
                 ("score_threshold", C.c_float), ("nms_thresh", C.c_float), ("range", C.c_float * 4),
                 ("out_boxes", C.c_void_p), ("out_scores", C.c_void_p), ("out_count", C.c_void_p), ("status", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class PillarArgs(C.Structure):
+    _fields_ = [("M", C.c_int32), ("P", C.c_int32), ("voxel_features", C.c_void_p), ("voxel_coords", C.c_void_p),
+                ("voxel_num_points", C.c_void_p), ("w", C.c_void_p), ("b", C.c_void_p),
+                ("voxel_size", C.c_float * 3), ("offset", C.c_float * 3),
+                ("nx", C.c_int32), ("ny", C.c_int32), ("n_agents", C.c_int32), ("canvas", C.c_void_p), ("channels_last", C.c_int32)]
 
 
 class StageWeights(C.Structure):
@@ -164,6 +171,8 @@ def load():
     lib.hmvit_postprocess_workspace_bytes.restype = C.c_size_t
     lib.hmvit_postprocess.argtypes = [C.POINTER(PostArgs), vp]
     lib.hmvit_postprocess.restype = C.c_int
+    lib.hmvit_pillar_scatter.argtypes = [C.POINTER(PillarArgs), vp]
+    lib.hmvit_pillar_scatter.restype = C.c_int
     for fn in ("hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
                "hmvit_bwd_wgrad", "hmvit_group_attn_bwd"):
         getattr(lib, fn).restype = C.c_int

@@ -13,6 +13,7 @@
 #include "qkv.cuh"
 #include "decoder.cuh"
 #include "postproc.cuh"
+#include "pillar.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -883,6 +884,31 @@ extern "C" int hmvit_postprocess(const HmvitPostArgs* a, void* stream) {
   post_iou_kernel<<<dim3(kPostMaskWords, kPostTop), 64, 0, st>>>(p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   post_nms_kernel<<<1, 32, 0, st>>>(p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// PointPillar front end (csrc/pillar.cuh)
+// ------------------------------------------------------------------------------------------------
+extern "C" int hmvit_pillar_scatter(const HmvitPillarArgs* a, void* stream) {
+  HMVIT_CHECK_ARG(a != nullptr, "pillar_scatter: null args");
+  HMVIT_CHECK_ARG(a->M >= 0 && a->P >= 1 && a->P <= kPfnMaxPts, "pillar_scatter: 1 <= P <= 32 point slots per pillar");
+  HMVIT_CHECK_ARG(a->nx > 0 && a->ny > 0 && a->n_agents > 0, "pillar_scatter: bad canvas shape");
+  HMVIT_CHECK_ARG(a->canvas && a->w && a->b, "pillar_scatter: null pointer");
+  HMVIT_CHECK_ARG(a->M == 0 || (a->voxel_features && a->voxel_coords && a->voxel_num_points), "pillar_scatter: null pointer");
+  HMVIT_CHECK_ARG((reinterpret_cast<uintptr_t>(a->voxel_features) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->voxel_coords) & 15) == 0,
+                  "pillar_scatter: voxel_features / voxel_coords must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HMVIT_CHECK_CUDA(cudaMemsetAsync(a->canvas, 0, static_cast<size_t>(a->n_agents) * kPfnOut * a->ny * a->nx * sizeof(float), st));
+  if (a->M == 0) return HMVIT_OK;
+  PillarParams p;
+  p.M = a->M; p.P = a->P; p.pts = a->voxel_features; p.coords = a->voxel_coords; p.npts = a->voxel_num_points;
+  p.w = a->w; p.b = a->b;
+  p.vx = a->voxel_size[0]; p.vy = a->voxel_size[1]; p.vz = a->voxel_size[2];
+  p.ox = a->offset[0]; p.oy = a->offset[1]; p.oz = a->offset[2];
+  p.nx = a->nx; p.ny = a->ny; p.n_agents = a->n_agents; p.canvas = a->canvas; p.channels_last = a->channels_last ? 1 : 0;
+  pillar_vfe_scatter_kernel<<<(a->M + 7) / 8, 256, 0, st>>>(p);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }

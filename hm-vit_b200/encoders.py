@@ -11,7 +11,8 @@ with the reference's constructor configs and state_dict keys (a reference checkp
 generator `tests/golden/make_golden_encoders.py` loads the SAME synthetic state dict into the unmodified reference modules).
 
 These modules are OUTSIDE the hot path `north_star` names: the arithmetic is torch / cuDNN library code on whatever device the
-tensors live on (convolutions, matmuls), not hand-written kernels -- SURVEY 8 f-3 ranks them "standard conv / attention,
+tensors live on (convolutions, matmuls), not hand-written kernels (one exception: PillarVFE + PointPillarScatter run as ONE
+hand-written kernel, `hmvit_pillar_scatter` in csrc/pillar.cuh, in eval mode on CUDA) -- SURVEY 8 f-3 ranks them "standard conv / attention,
 library-backed first".  What is ours is the host logic around the library calls: the pillar features are built and scattered
 without the reference's per-agent Python loops, the camera attention is evaluated in bounded chunks of agents instead of one
 (b, heads, Q, n K) tensor for the whole batch, and `CvtCameraEncoder` / `build_config3_model` compose BASELINE config 3 (CVT camera
@@ -208,17 +209,49 @@ class PointPillar(nn.Module):
         self.cls_head = nn.Conv2d(args['cls_head_dim'], args['anchor_number'], kernel_size=1)
         self.reg_head = nn.Conv2d(args['cls_head_dim'], 7 * args['anchor_number'], kernel_size=1)
         self.return_features = False
+        self.fused_front_end = True            # CUDA + eval: PillarVFE + scatter in one hand-written kernel
+        # canvas in torch's channels_last format: removes cuDNN's NCHW <-> NHWC passes around its tensor-core convolutions, but
+        # its NHWC BatchNorm inference kernel is 3.6 x slower than the NCHW one (measured: 3.63 vs 3.13 ms for the branch)
+        self.channels_last = False
 
     def set_return_features(self):
         self.return_features = True
         return self
+
+    def _fused_front_end(self, d):
+        """PillarVFE + PointPillarScatter as ONE hand-written kernel (`hmvit_pillar_scatter`, csrc/pillar.cuh) when the
+        configuration is the shipped yaml's (one PFN layer with BatchNorm, absolute xyz, no distance feature, <= 32 point
+        slots, 64 features), the module is in eval mode and the voxels are on the GPU; None otherwise (torch path)."""
+        vfe, sc = self.pillar_vfe, self.scatter
+        pts = d['voxel_features']
+        if (self.training or not pts.is_cuda or pts.dtype != torch.float32 or len(vfe.pfn_layers) != 1 or not vfe.use_norm
+                or not vfe.use_absolute_xyz or vfe.with_distance or pts.shape[1] > 32 or pts.shape[2] != 4
+                or vfe.num_filters[-1] != 64 or sc.num_bev_features != 64 or torch.is_grad_enabled()):
+            return None
+        from . import ops
+        pfn = vfe.pfn_layers[0]
+        s = pfn.norm.weight.float() / torch.sqrt(pfn.norm.running_var.float() + pfn.norm.eps)
+        w = (pfn.linear.weight.float() * s[:, None]).contiguous()                         # BatchNorm(eval) folded: [64][10]
+        b = (pfn.norm.bias.float() - pfn.norm.running_mean.float() * s).contiguous()
+        n = d.get('batch_size')
+        if n is None:
+            n = int(d['voxel_coords'][:, 0].max()) + 1
+        return ops.pillar_scatter(voxel_features=pts.contiguous(), voxel_coords=d['voxel_coords'].to(torch.int32).contiguous(),
+                                  voxel_num_points=d['voxel_num_points'].to(torch.int32).contiguous(), w=w, b=b,
+                                  voxel_size=vfe.voxel_xyz, offset=vfe.offset_xyz, nx=sc.nx, ny=sc.ny, n_agents=n,
+                                  channels_last=self.channels_last)
 
     def forward(self, data_dict):
         pl = data_dict['processed_lidar']
         d = {'voxel_features': pl['voxel_features'], 'voxel_coords': pl['voxel_coords'], 'voxel_num_points': pl['voxel_num_points']}
         if 'batch_size' in data_dict:
             d['batch_size'] = data_dict['batch_size']
-        feat = self.backbone(self.scatter(self.pillar_vfe(d)))['spatial_features_2d']
+        canvas = self._fused_front_end(d) if self.fused_front_end else None
+        if canvas is not None:
+            d['spatial_features'] = canvas
+        else:
+            d = self.scatter(self.pillar_vfe(d))
+        feat = self.backbone(d)['spatial_features_2d']
         if self.shrink_flag:
             feat = self.shrink_conv(feat)
         if self.return_features:

@@ -301,3 +301,27 @@ def postprocess(*, psm, rm, anchor_box, transformation_matrix, order_hwl, score_
     # the candidate count lives in the last 256 bytes of the workspace (csrc/api.cu)
     meta[2:3].copy_(ws[off + nbytes - 256: off + nbytes - 252].view(torch.int32))
     return boxes, scores, meta
+
+
+def pillar_scatter(*, voxel_features, voxel_coords, voxel_num_points, w, b, voxel_size, offset, nx, ny, n_agents,
+                   channels_last=False):
+    """PillarVFE (one PFN layer, BatchNorm folded into w / b) + PointPillarScatter in one kernel (include/hmvit_b200.h):
+    voxels -> canvas (n_agents, 64, ny, nx) fp32; with channels_last the same logical tensor in torch's channels_last
+    memory format."""
+    dev = voxel_features.device
+    M, P = int(voxel_features.shape[0]), int(voxel_features.shape[1])
+    if channels_last:
+        canvas = torch.empty(n_agents, ny, nx, 64, dtype=torch.float32, device=dev).permute(0, 3, 1, 2)
+    else:
+        canvas = torch.empty(n_agents, 64, ny, nx, dtype=torch.float32, device=dev)
+    args = _lib.PillarArgs()
+    args.M, args.P = M, P
+    args.voxel_features, args.voxel_coords, args.voxel_num_points = (voxel_features.data_ptr(), voxel_coords.data_ptr(),
+                                                                     voxel_num_points.data_ptr())
+    args.w, args.b = w.data_ptr(), b.data_ptr()
+    for k in range(3):
+        args.voxel_size[k], args.offset[k] = float(voxel_size[k]), float(offset[k])
+    args.nx, args.ny, args.n_agents, args.canvas = nx, ny, n_agents, canvas.data_ptr()
+    args.channels_last = 1 if channels_last else 0
+    _lib.check(_lib.load().hmvit_pillar_scatter(C.byref(args), _stream()))
+    return canvas

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMVIT_ABI_VERSION 7
+#define HMVIT_ABI_VERSION 8
 
 /* error codes */
 #define HMVIT_OK 0
@@ -366,6 +366,31 @@ typedef struct {
 } HmvitPostArgs;
 size_t hmvit_postprocess_workspace_bytes(int32_t H, int32_t W, int32_t A);
 int hmvit_postprocess(const HmvitPostArgs* args, void* stream);
+
+/* ---- PointPillar front end (LiDAR branch in front of the fusion) ------------------------------
+ * Replaces PillarVFE.forward (opencood/models/sub_modules/pillar_vfe.py:100-146) with ONE PFN layer
+ * (PFNLayer.forward, :32-54: Linear(10 -> 64, no bias) + BatchNorm1d in eval mode + ReLU + max over the point slots)
+ * for use_absolute_xyz = true, with_distance = false (the shipped yaml), and PointPillarScatter.forward
+ * (opencood/models/sub_modules/point_pillar_scatter.py:15-48) in one kernel: voxels -> dense canvas.
+ *   voxel_features  fp32 [M][P][4] (x, y, z, intensity; P <= 32 point slots, padded slots zero like the reference's input)
+ *   voxel_coords    int32 [M][4]   (agent, z, y, x)         voxel_num_points  int32 [M] (>= 1)
+ *   w               fp32 [64][10]  BatchNorm-folded weight  W * gamma / sqrt(var + eps)
+ *   b               fp32 [64]      BatchNorm-folded shift   beta - mean * gamma / sqrt(var + eps)
+ *   voxel_size / offset  fp32 [3]  (x, y, z): cell size and centre offset = size / 2 + range_min (pillar_vfe.py:85-90)
+ *   canvas          fp32 (n_agents, 64, ny, nx) -- or [n_agents][ny][nx][64] with channels_last != 0 (the memory format cuDNN's
+ *                   tensor-core convolutions use) --, overwritten (zero-filled, then the pillars' maxima)
+ * All pointers are device pointers.  Padded point slots contribute relu(b) to the maximum, as in the reference (it masks
+ * the features, not the outputs). */
+typedef struct {
+  int32_t M, P;
+  const float* voxel_features; const int32_t* voxel_coords; const int32_t* voxel_num_points;
+  const float* w; const float* b;
+  float voxel_size[3]; float offset[3];
+  int32_t nx, ny, n_agents;
+  float* canvas;
+  int32_t channels_last;
+} HmvitPillarArgs;
+int hmvit_pillar_scatter(const HmvitPillarArgs* args, void* stream);
 
 #ifdef __cplusplus
 }

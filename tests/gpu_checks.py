@@ -1362,4 +1362,50 @@ def check_config3_golden():
     return res
 
 
-CHECKS.update({"encoders_golden": check_encoders_golden, "config3_golden": check_config3_golden})
+def check_pillar_scatter():
+    """hmvit_pillar_scatter (PillarVFE + PointPillarScatter in one kernel, csrc/pillar.cuh) against the torch modules of the
+    same PointPillar (themselves pinned to the reference, test_encoders_cpu.py): the dense canvas, for pillars with 1..32
+    points incl. FULL pillars (no padded slot: the maximum may be negative before the ReLU), an agent without any pillar, and
+    through the whole PointPillar vs the reference golden.  Bar: max abs difference <= 1e-5 on the canvas (fp32, different
+    accumulation order of the 10 products)."""
+    S, G, enc, args, vox, cams, gold = _config3_parts()
+    la = args['lidar']
+    pp = enc.PointPillar(la).eval()
+    pp.load_state_dict(S.synth_module_state_dict(pp, 1), strict=True)
+    pp = pp.to(DEV).set_return_features()
+    nx, ny, _ = la['point_pillar_scatter']['grid_size']
+    v = S.synth_voxels(3, nx, ny, 500, la['lidar_range'], la['voxel_size'], seed=9)
+    keep = v['voxel_coords'][:, 0] != 1                                  # agent 1 has no pillar at all
+    v = {k: t[keep] for k, t in v.items()}
+    v['voxel_num_points'][::7] = 32                                      # full pillars
+    full = v['voxel_num_points'] == 32
+    g = torch.Generator().manual_seed(3)
+    v['voxel_features'][full] = v['voxel_features'][full] + (v['voxel_features'][full] == 0) * torch.rand(int(full.sum()), 32, 4, generator=g)
+    vd = {k: t.to(DEV) for k, t in v.items()}
+    with torch.no_grad():
+        d = {'voxel_features': vd['voxel_features'], 'voxel_coords': vd['voxel_coords'], 'voxel_num_points': vd['voxel_num_points'],
+             'batch_size': 3}
+        fused = pp._fused_front_end(dict(d))
+        assert fused is not None, "the fused front end must be taken for the shipped configuration on CUDA"
+        ref = pp.scatter(pp.pillar_vfe(dict(d)))['spatial_features']
+        pp.channels_last = True
+        fused_cl = pp._fused_front_end(dict(d))                          # same logical tensor, channels_last memory format
+        pp.channels_last = False
+        assert fused_cl.is_contiguous(memory_format=torch.channels_last) and torch.equal(fused_cl, fused)
+        # whole module, both paths, vs the reference golden
+        gv = {k: t.to(DEV) for k, t in vox.items()}
+        f1 = pp({'processed_lidar': gv, 'batch_size': 2})
+        pp.fused_front_end = False
+        f0 = pp({'processed_lidar': gv, 'batch_size': 2})
+    gp = torch.from_numpy(gold['pp_features'])
+    res = {"canvas_max_abs_diff": float((fused - ref).abs().max()), "canvas_nonzero_cells": int((ref != 0).any(1).sum()),
+           "empty_agent_zero": bool((fused[1] == 0).all()), "full_pillars": int(full.sum()),
+           "point_pillar_fused_rel_l2": rel_l2(f1.cpu(), gp), "point_pillar_torch_rel_l2": rel_l2(f0.cpu(), gp)}
+    assert tuple(fused.shape) == tuple(ref.shape) == (3, 64, ny, nx)
+    assert res["canvas_max_abs_diff"] <= 1e-5 and res["empty_agent_zero"] and res["full_pillars"] > 0, res
+    assert res["point_pillar_fused_rel_l2"] < 1e-3 and res["point_pillar_torch_rel_l2"] < 1e-3, res
+    return res
+
+
+CHECKS.update({"encoders_golden": check_encoders_golden, "config3_golden": check_config3_golden,
+               "pillar_scatter": check_pillar_scatter})
