@@ -407,6 +407,16 @@ def check_decoder_vs_oracle():
     rp2, rr2 = O.hetero_decoder(x2, mode[:1, 0], PD)
     res["clipped_psm_rel_l2"], res["clipped_rm_rel_l2"] = rel_l2(psm2.cpu(), rp2), rel_l2(rm2.cpu(), rr2)
     assert res["clipped_psm_rel_l2"] < 1e-3 and res["clipped_rm_rel_l2"] < 1e-3, res
+    # heights that are multiples of 8 but not of the 16-row tile: the second 8-row half of the last tile row lies outside
+    # the map (TMA zero fill on the way in, no store on the way out); incl. a map of a single half tile
+    for (h3, w3) in ((24, 40), (8, 8), (40, 16)):
+        x3 = torch.randn(2, 256, h3, w3)
+        with torch.no_grad():
+            psm3, rm3 = dec(x3.to(DEV), mode[:2].to(DEV), use_upsample=False)
+        rp3, rr3 = O.hetero_decoder(x3, mode[:2, 0], PD)
+        e3 = max(rel_l2(psm3.cpu(), rp3), rel_l2(rm3.cpu(), rr3))
+        res[f"half_tile_{h3}x{w3}_rel_l2"] = e3
+        assert e3 < 1e-3, res
     return res
 
 
