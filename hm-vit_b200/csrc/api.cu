@@ -811,7 +811,9 @@ extern "C" int hmvit_decoder_forward(const HmvitDecoderArgs* a, void* stream) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg::SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(conv3x3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg::SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv3x3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, DecCfg::SMEM_BYTES);
   });
   HMVIT_CHECK_CUDA(attr_err);
   const int N = a->H * a->W;
@@ -828,7 +830,14 @@ extern "C" int hmvit_decoder_forward(const HmvitDecoderArgs* a, void* stream) {
     ConvParams cp;
     cp.B = a->B; cp.H = a->H; cp.W = a->W; cp.ego_mode = a->ego_mode; cp.bias = a->conv_b + static_cast<size_t>(l) * 2 * 256;
     cp.out = act[(l + 1) & 1];
-    conv3x3_kernel<<<dim3(tiles, a->B), DecCfg::THREADS, DecCfg::SMEM_BYTES, st>>>(mx, mw, cp);
+    cp.head_w = a->head_w; cp.head_b = a->head_b; cp.psm = a->psm; cp.rm = a->rm; cp.n_cls = a->anchor_number;
+    if (l == a->num_convs - 1 && a->anchor_number == 2) {
+      // the shipped anchor_number: the two 1x1 heads run in the last layer's epilogue (no fp16 round trip of its output)
+      conv3x3_kernel<16><<<dim3(tiles, a->B), DecCfg::THREADS, DecCfg::SMEM_BYTES, st>>>(mx, mw, cp);
+      HMVIT_CHECK_CUDA(cudaGetLastError());
+      return HMVIT_OK;
+    }
+    conv3x3_kernel<0><<<dim3(tiles, a->B), DecCfg::THREADS, DecCfg::SMEM_BYTES, st>>>(mx, mw, cp);
     HMVIT_CHECK_CUDA(cudaGetLastError());
   }
   HeadsParams hp;

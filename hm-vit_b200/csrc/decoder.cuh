@@ -16,7 +16,10 @@
 //                             through a 3-stage 64 KB ring, two 128 x 256 fp32 accumulators (all 512 columns of tensor
 //                             memory), epilogue + bias, ReLU, fp16 pixel rows.  fp16 operands (11-bit significand, like the FFN of the fusion block): bf16
 //                             would put ~3e-3 per layer on the logits, the stated tolerance is 1e-3.
-//   det_heads_kernel          the 1x1 classification / regression heads on the last feature: fp32, thread == pixel.
+//                             The LAST layer (anchor_number == 2, the shipped yaml) keeps its rectified output rows in registers
+//                             (fp32) and applies the two 1x1 heads in its epilogue: no fp16 round trip, no heads launch.
+//   det_heads_kernel          the 1x1 classification / regression heads on the last feature as their own launch (other anchor
+//                             numbers): fp32, thread == pixel.
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
@@ -43,6 +46,12 @@ struct ConvParams {
   const int* ego_mode;         // [B] 0 = camera, 1 = lidar: which weight set a scene uses
   const float* bias;           // [2][256] BatchNorm-folded bias of this layer
   __half* out;                 // [B][H][W][256]
+  // last layer with the 1x1 heads in its epilogue (kHeadOut > 0): the layer's output is not stored
+  const float* head_w;         // [2][kHeadOut][256]
+  const float* head_b;         // [2][kHeadOut]
+  float* psm;                  // (B, n_cls, H W)
+  float* rm;                   // (B, kHeadOut - n_cls, H W)
+  int n_cls;
 };
 
 // 4-D tiled TMA load (channels, column, row, scene), completes on an mbarrier; out-of-range elements are zero-filled
@@ -53,7 +62,10 @@ HMVIT_DEVINL void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, i
       : "memory");
 }
 
-// grid (tiles_x * tiles_y, B)
+// grid (tiles_x * tiles_y, B).  kHeadOut > 0: the LAST layer -- its rectified output row stays in registers (fp32, not rounded
+// to fp16) and feeds the 1x1 classification / regression heads (kHeadOut = 8 x anchor_number outputs, fp32 FMA, weights staged
+// in the shared memory the operand ring no longer needs); nothing but psm / rm is written.
+template <int kHeadOut>
 __global__ void __launch_bounds__(DecCfg::THREADS, 1)
 conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const ConvParams p) {
   using Cfg = DecCfg;
@@ -127,6 +139,55 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
     const float* bias = p.bias + type * 256;
     mbar_wait_sleepy(acc_full, 0);
     tc_fence_after();
+    if constexpr (kHeadOut > 0) {
+      // every MMA has retired, so every operand stage has been read: stage 0 now holds the head weights of the ego's type
+      float* sHw = reinterpret_cast<float*>(smem);                 // [kHeadOut][256]
+      const float4* src = reinterpret_cast<const float4*>(p.head_w + static_cast<size_t>(type) * kHeadOut * 256);
+      for (int e = threadIdx.x - 64; e < kHeadOut * 64; e += 128) reinterpret_cast<float4*>(sHw)[e] = __ldg(src + e);
+      named_bar_sync(1, 128);
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        const int h = h0 + hf * 8 + (pix >> 4), w = w0 + (pix & 15);
+        const bool inside = h < p.H && w < p.W;
+        const uint32_t taddr = tm + hf * 256 + (static_cast<uint32_t>(q * 32) << 16);
+        float acc[kHeadOut];
+#pragma unroll
+        for (int o = 0; o < kHeadOut; ++o) acc[o] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + c * 32 + k));
+            v[k] = __float_as_uint(fmaxf(__uint_as_float(v[k]) + bb.x, 0.f));
+            v[k + 1] = __float_as_uint(fmaxf(__uint_as_float(v[k + 1]) + bb.y, 0.f));
+          }
+#pragma unroll
+          for (int o = 0; o < kHeadOut; ++o) {
+            const float* wrow = sHw + o * 256 + c * 32;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+              const float4 ww = *reinterpret_cast<const float4*>(wrow + k4 * 4);       // broadcast read
+              acc[o] = fmaf(__uint_as_float(v[k4 * 4]), ww.x, fmaf(__uint_as_float(v[k4 * 4 + 1]), ww.y,
+                       fmaf(__uint_as_float(v[k4 * 4 + 2]), ww.z, fmaf(__uint_as_float(v[k4 * 4 + 3]), ww.w, acc[o]))));
+            }
+          }
+        }
+        if (inside) {
+          const size_t N = static_cast<size_t>(p.H) * p.W, n = static_cast<size_t>(h) * p.W + w;
+          const float* hb = p.head_b + type * kHeadOut;
+          const int n_reg = kHeadOut - p.n_cls;
+#pragma unroll
+          for (int o = 0; o < kHeadOut; ++o) {
+            const float y = acc[o] + __ldg(hb + o);
+            if (o < p.n_cls) p.psm[(static_cast<size_t>(b) * p.n_cls + o) * N + n] = y;
+            else p.rm[(static_cast<size_t>(b) * n_reg + (o - p.n_cls)) * N + n] = y;
+          }
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c16 = 0; c16 < 16; ++c16) {
       const int hf = c16 >> 3, c = c16 & 7;
@@ -152,6 +213,7 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant
           *reinterpret_cast<uint4*>(orow + c * 32 + u * 8) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
+    }
     }
   }
   tc_fence_before();

@@ -417,6 +417,18 @@ def check_decoder_vs_oracle():
         e3 = max(rel_l2(psm3.cpu(), rp3), rel_l2(rm3.cpu(), rr3))
         res[f"half_tile_{h3}x{w3}_rel_l2"] = e3
         assert e3 < 1e-3, res
+    # anchor_number != 2: the heads run as their own launch (det_heads_kernel) instead of inside the last layer's epilogue
+    PD3 = O.synth_decoder_state_dict(13, anchor_number=3)
+    dec3 = pkg().HeteroDecoder({"input_dim": 256, "num_layer": 2, "num_ch_dec": [256, 256], "anchor_number": 3}).eval()
+    dec3.load_state_dict(PD3, strict=True)
+    dec3 = dec3.to(DEV)
+    x4 = torch.randn(2, 256, 16, 24)
+    with torch.no_grad():
+        psm4, rm4 = dec3(x4.to(DEV), mode[:2].to(DEV), use_upsample=False)
+    rp4, rr4 = O.hetero_decoder(x4, mode[:2, 0], PD3)
+    assert tuple(psm4.shape) == (2, 3, 16, 24) and tuple(rm4.shape) == (2, 21, 16, 24)
+    res["anchor3_psm_rel_l2"], res["anchor3_rm_rel_l2"] = rel_l2(psm4.cpu(), rp4), rel_l2(rm4.cpu(), rr4)
+    assert res["anchor3_psm_rel_l2"] < 1e-3 and res["anchor3_rm_rel_l2"] < 1e-3, res
     return res
 
 
