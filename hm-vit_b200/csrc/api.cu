@@ -8,6 +8,7 @@
 #include "attn_fa2.cuh"
 #include "attn_bwd.cuh"
 #include "bwd.cuh"
+#include "wgrad_tc.cuh"
 #include "dropout.cuh"
 #include "chain.cuh"
 #include "qkv.cuh"
@@ -725,6 +726,24 @@ extern "C" int hmvit_dropout(const float* a, const float* resid, float* out, int
   return HMVIT_OK;
 }
 
+// rows: the bf16 [n_rows][256] m-side operand the tensor map describes (M_ROWS) -- any valid pointer otherwise
+template <bool M_ROWS>
+static int launch_wgrad_tc(const void* rows, long long n_rows, const WgradTcParams& q, cudaStream_t st) {
+  using Cfg = WgTc<M_ROWS>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(wgrad_tc_kernel<M_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (M_ROWS) { int rc = make_weight_tmap(&map, rows, n_rows, 2, 64); if (rc) return rc; }
+  wgrad_tc_kernel<M_ROWS><<<num_sms(), Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(map, q);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
 extern "C" int hmvit_bwd_wgrad(const HmvitWgradArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a != nullptr, "bwd_wgrad: null args");
   HMVIT_CHECK_ARG(a->B > 0 && a->L > 0 && a->N > 0 && a->B * a->L <= 65535, "bwd_wgrad: bad shape");
@@ -732,6 +751,18 @@ extern "C" int hmvit_bwd_wgrad(const HmvitWgradArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a->mode && a->record_len && a->a && a->b && a->dw, "bwd_wgrad: null pointer");
   HMVIT_CHECK_ARG(a->dw_rows >= 256 && a->dw_row0 >= 0 && a->dw_row0 + 256 <= a->dw_rows, "bwd_wgrad: bad dw window");
   HMVIT_CHECK_ARG(!(a->b_stats != nullptr && a->b_rows_bf16), "bwd_wgrad: b_stats needs a cm B operand");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // tcgen05 form (wgrad_tc.cuh): B from a cm tensor, whole 64-token tiles, agent list that fits its shared-memory table
+  if (!a->b_rows_bf16 && a->N % 64 == 0 && a->B * a->L <= 2048) {
+    WgradTcParams q;
+    q.L = a->L; q.N = a->N; q.n_agents = a->B * a->L; q.mode = a->mode; q.record_len = a->record_len;
+    q.ego_only = a->ego_only ? 1 : 0;
+    q.m_cm = static_cast<const float*>(a->a); q.n_cm = static_cast<const float*>(a->b);
+    q.n_stats = reinterpret_cast<const float2*>(a->b_stats);
+    q.dw = a->dw; q.dw_rows = a->dw_rows; q.dw_row0 = a->dw_row0;
+    if (a->a_rows_bf16) return launch_wgrad_tc<true>(a->a, static_cast<long long>(a->B) * a->L * a->N, q, st);
+    return launch_wgrad_tc<false>(a->b, 256, q, st);
+  }
   WgradParams p;
   p.L = a->L; p.N = a->N; p.mode = a->mode; p.record_len = a->record_len; p.ego_only = a->ego_only ? 1 : 0;
   p.a_cm = static_cast<const float*>(a->a); p.a_rows = static_cast<const __nv_bfloat16*>(a->a);
@@ -739,7 +770,6 @@ extern "C" int hmvit_bwd_wgrad(const HmvitWgradArgs* a, void* stream) {
   p.b_stats = reinterpret_cast<const float2*>(a->b_stats);
   p.dw = a->dw; p.dw_rows = a->dw_rows; p.dw_row0 = a->dw_row0; p.tok_chunk = 2048;
   dim3 grid(4, (a->N + p.tok_chunk - 1) / p.tok_chunk, a->B * a->L);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (a->a_rows_bf16 && a->b_rows_bf16) wgrad_kernel<true, true><<<grid, 256, 0, st>>>(p);
   else if (a->a_rows_bf16) wgrad_kernel<true, false><<<grid, 256, 0, st>>>(p);
   else if (a->b_rows_bf16) wgrad_kernel<false, true><<<grid, 256, 0, st>>>(p);
