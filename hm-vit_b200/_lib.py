@@ -12,13 +12,13 @@ LIB_PATH = os.environ.get("HMVIT_LIB", os.path.join(_HERE, "libhmvit_b200.so")) 
 GEMM_QKV, GEMM_OUT, GEMM_FFN1, GEMM_FFN2, GEMM_HEAD1, GEMM_HEAD2, GEMM_QKV_NOLN = range(7)
 GEMM_LN_LIN_CM, GEMM_LIN_CM, GEMM_LIN_ROWS, GEMM_ROWS_LIN_CM = range(7, 11)
 ATTN_FUSED, ATTN_SPLIT, ATTN_SINGLE = range(3)     # HmvitAttnArgs.impl
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 EXPORTS = (
     "hmvit_abi_version", "hmvit_last_error", "hmvit_rowgemm", "hmvit_group_attn", "hmvit_warp_bilinear",
     "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
     "hmvit_out_ffn_chain", "hmvit_ffn_head",
-    "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum",
+    "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum", "hmvit_bwd_dgrad_cat",
     "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes", "hmvit_dropout", "hmvit_attn_records",
     "hmvit_decoder_workspace_bytes", "hmvit_decoder_forward", "hmvit_postprocess_workspace_bytes", "hmvit_postprocess", "hmvit_pillar_scatter",
 )
@@ -160,6 +160,8 @@ def load():
     lib.hmvit_bwd_cast_bf16.argtypes = [vp, vp, C.c_size_t, vp]
     lib.hmvit_bwd_colsum.argtypes = [vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp]
     lib.hmvit_bwd_wgrad.argtypes = [C.POINTER(WgradArgs), vp]
+    lib.hmvit_bwd_dgrad_cat.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
+    lib.hmvit_bwd_dgrad_cat.restype = C.c_int
     lib.hmvit_dropout.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, C.c_uint64, C.c_uint32, C.c_float, vp]
     lib.hmvit_dropout.restype = C.c_int
     lib.hmvit_group_attn_bwd.argtypes = [C.POINTER(AttnBwdArgs), vp]

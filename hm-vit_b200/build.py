@@ -4,7 +4,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["csrc/api.cu"]
-HEADERS = ["csrc/common.cuh", "csrc/rowgemm.cuh", "csrc/attn.cuh", "csrc/attn_split.cuh", "csrc/attn_fused.cuh", "csrc/attn_fa2.cuh", "csrc/attn_bwd.cuh", "csrc/bwd.cuh", "csrc/wgrad_tc.cuh", "csrc/dropout.cuh", "csrc/wmma_shared.cuh", "csrc/chain.cuh", "csrc/qkv.cuh", "csrc/decoder.cuh", "csrc/postproc.cuh", "csrc/pillar.cuh", "../include/hmvit_b200.h"]
+HEADERS = ["csrc/common.cuh", "csrc/rowgemm.cuh", "csrc/attn.cuh", "csrc/attn_split.cuh", "csrc/attn_fused.cuh", "csrc/attn_fa2.cuh", "csrc/attn_bwd.cuh", "csrc/bwd.cuh", "csrc/wgrad_tc.cuh", "csrc/dgrad_cat.cuh", "csrc/dropout.cuh", "csrc/wmma_shared.cuh", "csrc/chain.cuh", "csrc/qkv.cuh", "csrc/decoder.cuh", "csrc/postproc.cuh", "csrc/pillar.cuh", "../include/hmvit_b200.h"]
 OUTPUT = os.path.join(_HERE, "libhmvit_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC"]

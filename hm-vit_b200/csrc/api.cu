@@ -9,6 +9,7 @@
 #include "attn_bwd.cuh"
 #include "bwd.cuh"
 #include "wgrad_tc.cuh"
+#include "dgrad_cat.cuh"
 #include "dropout.cuh"
 #include "chain.cuh"
 #include "qkv.cuh"
@@ -774,6 +775,29 @@ extern "C" int hmvit_bwd_wgrad(const HmvitWgradArgs* a, void* stream) {
   else if (a->a_rows_bf16) wgrad_kernel<true, false><<<grid, 256, 0, st>>>(p);
   else if (a->b_rows_bf16) wgrad_kernel<false, true><<<grid, 256, 0, st>>>(p);
   else wgrad_kernel<false, false><<<grid, 256, 0, st>>>(p);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
+extern "C" int hmvit_bwd_dgrad_cat(const void* dcat, const void* w0, const void* w1, float* out, int32_t B, int32_t L, int32_t N,
+                                   const int32_t* mode, const int32_t* record_len, void* stream) {
+  HMVIT_CHECK_ARG(B > 0 && L > 0 && N > 0 && B * L <= DgradCatCfg::MAX_AGENTS, "bwd_dgrad_cat: bad shape (B*L <= 2048)");
+  HMVIT_CHECK_ARG(dcat && w0 && w1 && out && mode && record_len, "bwd_dgrad_cat: null pointer");
+  const long long R = static_cast<long long>(B) * L * N;
+  HMVIT_CHECK_ARG(5 * R + 128 < (1ll << 31), "bwd_dgrad_cat: too many rows for the tensor-map coordinates");
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(dgrad_cat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DgradCatCfg::SMEM_BYTES);
+  });
+  HMVIT_CHECK_CUDA(attr_err);
+  CUtensorMap am, m0, m1;
+  int rc = make_weight_tmap(&am, dcat, 5 * R, 2, 128); if (rc) return rc;
+  rc = make_weight_tmap(&m0, w0, 1280, 2, 256); if (rc) return rc;
+  rc = make_weight_tmap(&m1, w1, 1280, 2, 256); if (rc) return rc;
+  DgradCatParams q;
+  q.L = L; q.N = N; q.n_agents = B * L; q.R = R; q.mode = mode; q.record_len = record_len; q.out = out;
+  dgrad_cat_kernel<<<num_sms(), DgradCatCfg::THREADS, DgradCatCfg::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(am, m0, m1, q);
   HMVIT_CHECK_CUDA(cudaGetLastError());
   return HMVIT_OK;
 }

@@ -196,6 +196,14 @@ def bwd_wgrad(a, b, dw, *, B, L, N, mode, record_len, ego_only=False, b_stats=No
     return dw
 
 
+def bwd_dgrad_cat(dcat, w0, w1, out, *, B, L, N, mode, record_len):
+    """out[a] (256, N) = sum_p dcat[p, rows of a] @ w[type][p*256:(p+1)*256].T, transposed to cm: the input gradient of the fused
+    Q | K' | V' projection as ONE K = 1280 GEMM.  dcat bf16 (5, B*L*N, 256); w0 / w1 bf16 (1280, 256); out cm fp32."""
+    _lib.check(_lib.load().hmvit_bwd_dgrad_cat(dcat.data_ptr(), w0.data_ptr(), w1.data_ptr(), out.data_ptr(), B, L, N,
+                                               mode.data_ptr(), record_len.data_ptr(), _stream()))
+    return out
+
+
 def group_attn_bwd(*, B, L, H, W, kind, mode, record_len, cav_mask, T, cell, q, k, v, bk, bv, bias_table, o, d_o, lse,
                    dq, dk, dv, dbk, dbv, dbias_table, ego_only=False):
     args = _lib.AttnBwdArgs()

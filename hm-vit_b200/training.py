@@ -122,8 +122,8 @@ def kernel_pack_stage(F: Dict[str, torch.Tensor], rows_dtype) -> Dict[str, torch
         pk[f"waT{t}"] = _tf32(F["wa"][t].t(), exact)
         pk[f"w1T{t}"] = _tf32(F["w1"][t].t(), exact)
         pk[f"w2T{t}"] = _tf32(F["w2"][t].t(), exact)
-        for p in range(5):
-            pk[f"wcatT{p}_{t}"] = _lowp(F["wcat"][t][p * Cd:(p + 1) * Cd].t(), rows_dtype)
+        # input gradient of the fused projection as one K = 1280 GEMM: rows p*256.. = transposed plane p of W_cat
+        pk[f"wcatT_{t}"] = _lowp(torch.cat([F["wcat"][t][p * Cd:(p + 1) * Cd].t() for p in range(5)], 0), rows_dtype)
     for k in ("bcat", "bk", "bv", "ba", "b1", "b2", "bias_table"):
         pk[k] = F[k].detach().float().contiguous()
     return pk
@@ -328,8 +328,7 @@ def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xl
         for p in range(5):
             ops.bwd_wgrad(dcat[p], xin, g["wcat"], b_stats=st, row0=p * C_DIM, **common)
             ops.bwd_colsum(dcat[p], g["bcat"][:, p * C_DIM:], **common)
-            ops.rowgemm(_lib.GEMM_ROWS_LIN_CM, n_out=C_DIM, a=dcat[p], w0=pk[f"wcatT{p}_0"], w1=pk[f"wcatT{p}_1"], bias=zero_b,
-                        resid=dz if p > 0 else None, out=dz, **common)
+        ops.bwd_dgrad_cat(dcat, pk["wcatT_0"], pk["wcatT_1"], dz, **common)
         ops.bwd_layernorm(dz, xin, st, dX, dX, **geo3)                 # dX: gradient w.r.t. the stage input
     return dX, grads, head_grads
 

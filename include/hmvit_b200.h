@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define HMVIT_ABI_VERSION 8
+#define HMVIT_ABI_VERSION 9
 
 /* error codes */
 #define HMVIT_OK 0
@@ -296,6 +296,15 @@ typedef struct {
   int32_t dw_rows, dw_row0;
 } HmvitWgradArgs;
 int hmvit_bwd_wgrad(const HmvitWgradArgs* args, void* stream);
+
+/* input gradient of the fused typed Q | K' | V' projection (adjoint of the GEMM of hmvit_rowgemm variant QKV;
+ * autograd through HeteroAttention.to_qkv, opencood/models/sub_modules/hetero_fusion.py:111-132), ONE K = 1280 GEMM:
+ *   out[a][c][tok] = sum_p sum_k dcat[p][a*N + tok][k] * w[type(a)][p*256 + c][k]
+ * dcat: bf16 [5][B*L*N][256] (planes Q, K'|te=0, K'|te=1, V'|te=0, V'|te=1); w0 / w1: bf16 [1280][256], rows p*256.. hold
+ * the TRANSPOSED plane p of the folded W_cat of type 0 / 1; out: cm fp32 [B*L][256][N], overwritten for every valid agent
+ * (all valid agents: they are K/V sources even in the dead-query stage).  B*L <= 2048. */
+int hmvit_bwd_dgrad_cat(const void* dcat, const void* w0, const void* w1, float* out, int32_t B, int32_t L, int32_t N,
+                        const int32_t* mode, const int32_t* record_len, void* stream);
 
 /* backward of hmvit_group_attn: same geometry arguments; q/k/v/o are the forward tensors, d_o the gradient of the
  * forward output, lse the statistics saved by the forward.  dq [R][256], dk / dv [2][R][256], dbk / dbv [2][2][256],

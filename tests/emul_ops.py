@@ -211,6 +211,16 @@ def _operand(t, ai, N):
     return t[ai * N:(ai + 1) * N].float() if t.dim() == 2 else t[ai].t()
 
 
+def bwd_dgrad_cat(dcat, w0, w1, out, *, B, L, N, mode, record_len):
+    w = (w0.float(), w1.float())
+    mode = mode.reshape(-1)
+    for b, l, ai in _agents(B, L, record_len, False):
+        t = int(mode[ai] != 0)
+        y = sum(dcat[p, ai * N:(ai + 1) * N].float() @ w[t][p * C:(p + 1) * C].t() for p in range(5))
+        out[ai] = y.t()
+    return out
+
+
 def bwd_wgrad(a, b, dw, *, B, L, N, mode, record_len, ego_only=False, b_stats=None, row0=0):
     mode = mode.reshape(-1)
     for bb, l, ai in _agents(B, L, record_len, ego_only):

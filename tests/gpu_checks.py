@@ -820,6 +820,29 @@ def check_bwd_wgrad():
     return res
 
 
+def check_bwd_dgrad_cat():
+    """input gradient of the fused Q | K' | V' projection as one K = 1280 GEMM (csrc/dgrad_cat.cuh) against the emulation on the
+    same bf16 operands; 16 x 24 (whole 128-token tiles) and 24 x 24 (576 tokens: a half tile at the end of every agent)."""
+    ops = pkg().ops
+    res = {}
+    for name, kw in (("16x24", {}), ("24x24", dict(H=24, W=24))):
+        g = _geo_small(seed=11, **kw)
+        B, L, N = g["B"], g["L"], g["N"]
+        gen = torch.Generator().manual_seed(5)
+        dcat = torch.randn(5, B * L * N, 256, generator=gen).to(torch.bfloat16)
+        w = [(torch.randn(1280, 256, generator=gen) / 16).to(torch.bfloat16) for _ in range(2)]
+        ref = torch.full((B * L, 256, N), 7.0)
+        EM.bwd_dgrad_cat(dcat, w[0], w[1], ref, B=B, L=L, N=N, mode=g["mode"], record_len=g["rl"])
+        out = torch.full((B * L, 256, N), 7.0, device=DEV)
+        ops.bwd_dgrad_cat(dcat.to(DEV), w[0].to(DEV), w[1].to(DEV), out, B=B, L=L, N=N, mode=g["mode"].to(DEV), record_len=g["rl"].to(DEV))
+        res[name] = rel_l2(out.cpu(), ref)
+        pad = [ai for ai in range(B * L) if ai % L >= int(g["rl"][ai // L])]
+        assert pad and all(bool((out[ai] == 7.0).all()) for ai in pad), "padded slots must stay untouched"
+    torch.cuda.synchronize()
+    assert all(v < 1e-5 for v in res.values()), res          # same bf16 operands, fp32 accumulate: summation order only
+    return res
+
+
 def check_bwd_lin_variants():
     """the row-GEMM variants the backward uses (7-10) against the emulation with equally rounded operands."""
     p = pkg()
@@ -1042,7 +1065,7 @@ def check_train_api():
 
 
 CHECKS.update({"bwd_small_kernels": check_bwd_small_kernels, "bwd_wgrad": check_bwd_wgrad,
-               "bwd_lin_variants": check_bwd_lin_variants, "attn_bwd": check_attn_bwd,
+               "bwd_lin_variants": check_bwd_lin_variants, "bwd_dgrad_cat": check_bwd_dgrad_cat, "attn_bwd": check_attn_bwd,
                "train_grads_small": check_train_grads_small, "train_api": check_train_api,
                "attn_split_vs_single": check_attn_split_vs_single})
 

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(pkg._lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert pkg._lib.load().hmvit_abi_version() == pkg._lib.ABI_VERSION == 8
+    assert pkg._lib.load().hmvit_abi_version() == pkg._lib.ABI_VERSION == 9
 
 
 def test_state_dict_keys_match_reference_spec():
