@@ -753,14 +753,18 @@ extern "C" int hmvit_bwd_wgrad(const HmvitWgradArgs* a, void* stream) {
   HMVIT_CHECK_ARG(a->dw_rows >= 256 && a->dw_row0 >= 0 && a->dw_row0 + 256 <= a->dw_rows, "bwd_wgrad: bad dw window");
   HMVIT_CHECK_ARG(!(a->b_stats != nullptr && a->b_rows_bf16), "bwd_wgrad: b_stats needs a cm B operand");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // tcgen05 form (wgrad_tc.cuh): B from a cm tensor, whole 64-token tiles, agent list that fits its shared-memory table
-  if (!a->b_rows_bf16 && a->N % 64 == 0 && a->B * a->L <= 2048) {
+  // tcgen05 form (wgrad_tc.cuh): at least one cm operand, whole 64-token tiles, agent list that fits its shared-memory table
+  if (!(a->a_rows_bf16 && a->b_rows_bf16) && a->N % 64 == 0 && a->B * a->L <= 2048) {
     WgradTcParams q;
     q.L = a->L; q.N = a->N; q.n_agents = a->B * a->L; q.mode = a->mode; q.record_len = a->record_len;
     q.ego_only = a->ego_only ? 1 : 0;
     q.m_cm = static_cast<const float*>(a->a); q.n_cm = static_cast<const float*>(a->b);
     q.n_stats = reinterpret_cast<const float2*>(a->b_stats);
-    q.dw = a->dw; q.dw_rows = a->dw_rows; q.dw_row0 = a->dw_row0;
+    q.dw = a->dw; q.dw_rows = a->dw_rows; q.dw_row0 = a->dw_row0; q.swapped = 0;
+    if (a->b_rows_bf16) {        // B rows, A cm: exchange the operands (dW^T = B^T A), the flush writes transposed
+      q.n_cm = static_cast<const float*>(a->a); q.m_cm = nullptr; q.swapped = 1;
+      return launch_wgrad_tc<true>(a->b, static_cast<long long>(a->B) * a->L * a->N, q, st);
+    }
     if (a->a_rows_bf16) return launch_wgrad_tc<true>(a->a, static_cast<long long>(a->B) * a->L * a->N, q, st);
     return launch_wgrad_tc<false>(a->b, 256, q, st);
   }

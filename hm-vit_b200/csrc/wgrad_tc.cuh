@@ -6,8 +6,9 @@
 //   HeteroAttention.to_qkv / to_out     hetero_fusion.py:111-152
 //   HeteroFeedForward                   base_transformer.py:180-192
 // (gradients of the FOLDED weights).  Same contract as wgrad_kernel (bwd.cuh, warp-level
-// wmma tiles, 145 TFLOP/s) which stays for the one operand combination this kernel does not take (B as bf16 rows)
-// and as the independently written cross-check.
+// wmma tiles, 145 TFLOP/s) which stays for shapes this kernel does not take (both operands bf16 rows, N % 64 != 0,
+// more than 2048 agent slots) and as the independently written cross-check.  A bf16-rows B operand with a cm A operand
+// runs with the operands exchanged (`swapped`: the accumulator then holds dW itself and the flush is strided).
 //
 // The contraction runs over TOKENS (K = all tokens of a type, ~170 k at the bench shape) and the output is one
 // 256 x 256 matrix per type, so the kernel is bound by reading its operands once: 346 MB (fp32 cm) + 173 MB
@@ -40,6 +41,8 @@ struct WgradTcParams {
   const float2* n_stats;          // optional: normalise the n-side operand with per-token (mean, rstd)
   float* dw;                      // [2][dw_rows][256] fp32, accumulated
   int dw_rows, dw_row0;
+  int swapped;                    // the caller exchanged the operands (math B is bf16 rows): D' holds dW itself, not its
+                                  // transpose -- lane = dW row, column = dW column (strided reductions in the flush)
 };
 
 template <bool M_ROWS>
@@ -48,7 +51,9 @@ struct WgTc {
   static constexpr int NS = 3;                      // ring stages
   static constexpr int OP_BYTES = 256 * 128;        // one operand tile: 256 channels x 64 tokens, bf16
   static constexpr int STAGE_BYTES = 2 * OP_BYTES;
-  static constexpr int NW_STAGE = M_ROWS ? 8 : 16;  // stager warps (8 per register-staged operand)
+  static constexpr int NW_STAGE = 16;               // stager warps: 8 per register-staged operand, or (M_ROWS) two groups of 8
+                                                    // that take alternate tiles (twice the loads in flight)
+  static constexpr int NW_TILE = M_ROWS ? 8 : 16;   // stager warps that arrive on a stage's full barrier
   static constexpr int THREADS = (NW_STAGE + 2) * 32;
   static constexpr int MAX_AGENTS = 2048;
   static constexpr int OFF_BARS = NS * STAGE_BYTES;
@@ -73,7 +78,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap m_map, const WgradTcParams p
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::NS; ++s) { mbar_init(&full[s], Cfg::NW_STAGE + (M_ROWS ? 1 : 0)); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < Cfg::NS; ++s) { mbar_init(&full[s], Cfg::NW_TILE + (M_ROWS ? 1 : 0)); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, Cfg::NW_STAGE);
     fence_mbar_init();
@@ -115,14 +120,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap m_map, const WgradTcParams p
       constexpr int RANGE = 512 / (Cfg::NW_STAGE / 4);             // columns per warp
       const int q = warp & 3, col0 = (warp >> 2) * RANGE;
       const int h = col0 >> 8, m0 = col0 & 255;
-      float* dst = p.dw + (static_cast<size_t>(type) * p.dw_rows + p.dw_row0 + m0) * kC + h * 128 + q * 32 + lane;
+      const int nl = h * 128 + q * 32 + lane;                      // this thread's n-side channel
+      float* dst = p.dw + (static_cast<size_t>(type) * p.dw_rows + p.dw_row0) * kC +
+                   (p.swapped ? static_cast<size_t>(nl) * kC + m0 : static_cast<size_t>(m0) * kC + nl);
 #pragma unroll 1
       for (int c = 0; c < RANGE; c += 32) {
         uint32_t r[32];
         tmem_ld32(tm + (static_cast<uint32_t>(q * 32) << 16) + col0 + c, r);
         tmem_ld_wait();
+        if (p.swapped) {                  // 32 consecutive floats of one dW row per thread: 128-bit vector reductions
 #pragma unroll
-        for (int k = 0; k < 32; ++k) atomicAdd(dst + static_cast<size_t>(c + k) * kC, __uint_as_float(r[k]));
+          for (int k = 0; k < 32; k += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c + k), "f"(__uint_as_float(r[k])),
+                         "f"(__uint_as_float(r[k + 1])), "f"(__uint_as_float(r[k + 2])), "f"(__uint_as_float(r[k + 3])) : "memory");
+        } else {                          // one dW row per register, the warp's lanes cover 32 consecutive columns
+#pragma unroll
+          for (int k = 0; k < 32; ++k) atomicAdd(dst + static_cast<size_t>(c + k) * kC, __uint_as_float(r[k]));
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -136,6 +150,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap m_map, const WgradTcParams p
       const int e = sList[ai], a = e & 0x7fff, type = e >> 15;
       if (cur_type >= 0 && type != cur_type) { flush(cur_type, seg); ++seg; }
       cur_type = type;
+      if (M_ROWS && (i & 1u) != static_cast<uint32_t>(warp >> 3)) continue;      // the other group's tile
       const int tok0 = kt * Cfg::KT;
       const float* src = src_base + (static_cast<size_t>(a) * kC + r0) * p.N + tok0 + u * 8;
       float4 v[16];
