@@ -19,7 +19,8 @@
 #include "attn.cuh"
 #include "wmma_shared.cuh"
 
-#ifndef HMVIT_BWD_DBG   // bottleneck-hunting builds only (results are wrong): 1 no shared bias-gradient atomics, 2 no global scatter
+#ifndef HMVIT_BWD_DBG   // bottleneck-hunting builds only (results are wrong): 1 no shared bias-gradient atomics, 2 no global scatter,
+                        // 4 no per-step warp barrier in the probability loop, 8 no probability loop, 16 no K/V re-gather, 32 no tensor-core tiles
 #define HMVIT_BWD_DBG 0
 #endif
 
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
           const int s = tt * 16 + warp * 2 + hlf;
           const TapRec rec = sTap[s];
           uint4 ko = make_uint4(0, 0, 0, 0), vo = make_uint4(0, 0, 0, 0);
-          if ((rec.w01 | rec.w23) != 0u) {
+          if (!(HMVIT_BWD_DBG & 16) && (rec.w01 | rec.w23) != 0u) {
             const uint32_t wq[4] = {rec.w01 & 0xffffu, rec.w01 >> 16, rec.w23 & 0xffffu, rec.w23 >> 16};
             ko = make_uint4(bk2[0], bk2[1], bk2[2], bk2[3]);
             vo = make_uint4(bv2[0], bv2[1], bv2[2], bv2[3]);
@@ -245,28 +246,41 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
         __syncwarp();
         // ---- probabilities and logit gradients ----
         // The relative position bias gradient goes into a table PRIVATE to this warp with plain read-modify-writes
-        // (shared-memory float atomics cost 22 % of the kernel).  Lane mapping: lanes 0-15 take query row s, lanes
-        // 16-31 row (s + 16) ^ 1 -- two window rows further down, column parity flipped: the 32 (query, key) pairs
-        // of one step then hit 32 different table entries and conflict-free banks of the [64][16] scratch tiles.
+        // (shared-memory float atomics cost 22 % of the kernel).  This loop was 32 % of the kernel and issue-bound (two warps
+        // per scheduler, ~40 instructions per logit), so a lane takes TWO adjacent keys of the chunk (one 64-bit load of S / dP,
+        // one packed bf16x2 store of P / dS, the query's lse / D and the index arithmetic shared) for one query per step:
+        // lane = (q, key pair kp), query row 2 q + (e >> 3), column (e & 7) ^ (q & 1).  The four queries of a step lie in
+        // different window rows (2 q - key row is distinct over (q, key row)), so the 64 (query, key) pairs of a step hit 64
+        // different table entries; the column flip of odd q keeps the 64-bit scratch reads of a half-warp on different banks.
         float* sBgW = sBgrad + warp * kBiasStride;
+        {
+          const int kp = lane & 7, qs = lane >> 3;
+          const int kk0 = kp * 2, sp0 = kc * 16 + kk0;            // keys sp0, sp0 + 1 (same key row)
+          const TapRec rk0 = sTap[sp0], rk1 = sTap[sp0 + 1];
+          const bool v0 = (rk0.w01 | rk0.w23) != 0u, v1 = (rk1.w01 | rk1.w23) != 0u;
+          const int ky = sp0 >> 3, kx0 = sp0 & 7;
+          const float* sBiasH = sBias + hl * kBiasStride;
 #pragma unroll 4
-        for (int e = 0; e < 32; ++e) {
-          const int sA = (e >> 4) * 32 + (e & 15);
-          const int s = lane < 16 ? sA : ((sA + 16) ^ 1);
-          const int kk = lane & 15, idx = s * 16 + kk, sp = kc * 16 + kk;
-          const TapRec rec = sTap[sp];
-          float pr = 0.f, dsn = 0.f;
-          if ((rec.w01 | rec.w23) != 0u) {
-            const int rel = ((s >> 3) - (sp >> 3) + 7) * 15 + ((s & 7) - (sp & 7) + 7);
-            pr = ex2(sS[idx] + sBias[hl * kBiasStride + rel] - sLse[hl * kS + s]);
-            dsn = pr * (sdP[idx] - sD[hl * kS + s]);
+          for (int e = 0; e < ((HMVIT_BWD_DBG & 8) ? 0 : 16); ++e) {
+            const int sy = 2 * qs + (e >> 3), sx = (e & 7) ^ (qs & 1);
+            const int s = sy * 8 + sx, idx = s * 16 + kk0;
+            const int rel = (sy - ky + 7) * 15 + (sx - kx0 + 7);  // of key sp0; key sp0 + 1: rel - 1 (>= 0: kx0 + 1 <= 7)
+            const float2 sv = *reinterpret_cast<const float2*>(sS + idx);
+            const float2 dp = *reinterpret_cast<const float2*>(sdP + idx);
+            const float l2 = sLse[hl * kS + s], dd = sD[hl * kS + s];
+            float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+            if (v0) { p0 = ex2(sv.x + sBiasH[rel] - l2); d0 = p0 * (dp.x - dd); }
+            if (v1) { p1 = ex2(sv.y + sBiasH[rel - 1] - l2); d1 = p1 * (dp.y - dd); }
 #if !(HMVIT_BWD_DBG & 1)
-            sBgW[rel] += dsn;
+            if (v0) sBgW[rel] += d0;
+            if (v1) sBgW[rel - 1] += d1;
+#endif
+            *reinterpret_cast<uint32_t*>(sPb + idx) = pack_bf16x2(p0, p1);
+            *reinterpret_cast<uint32_t*>(sdSb + idx) = pack_bf16x2(d0 * 0.69314718055994530942f, d1 * 0.69314718055994530942f);
+#if !(HMVIT_BWD_DBG & 4)
+            __syncwarp();                                        // the next step may touch the same table entry from another lane
 #endif
           }
-          sPb[idx] = __float2bfloat16(pr);
-          sdSb[idx] = __float2bfloat16(dsn * 0.69314718055994530942f);
-          __syncwarp();                                          // the next step may touch the same table entry from another lane
         }
         __syncwarp();
         // ---- dQ_h += dS Kg_h ----
