@@ -180,28 +180,28 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
           bk2[0] = pack_bf16x2(k0.x, k0.y); bk2[1] = pack_bf16x2(k0.z, k0.w); bk2[2] = pack_bf16x2(k1.x, k1.y); bk2[3] = pack_bf16x2(k1.z, k1.w);
           bv2[0] = pack_bf16x2(v0.x, v0.y); bv2[1] = pack_bf16x2(v0.z, v0.w); bv2[2] = pack_bf16x2(v1.x, v1.y); bv2[3] = pack_bf16x2(v1.z, v1.w);
         }
-        for (int tt = 0; tt < 4; ++tt) {
-          const int s = tt * 16 + warp * 2 + hlf;
-          const TapRec rec = sTap[s];
+        // The tap loads of token tt + 1 are issued before token tt is blended (two register images of the eight 16-byte
+        // taps): the four tokens of a half-warp exposed four global round trips per source, 17 % of the kernel.
+        auto load_taps = [&](const TapRec& rec, uint4 (&kk)[4], uint4 (&vv)[4]) {
+          const uint32_t wq[4] = {rec.w01 & 0xffffu, rec.w01 >> 16, rec.w23 & 0xffffu, rec.w23 >> 16};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            kk[q] = make_uint4(0, 0, 0, 0); vv[q] = make_uint4(0, 0, 0, 0);
+            if (!(HMVIT_BWD_DBG & 16) && wq[q] != 0u) {
+              const int yy = rec.y0 + (q >> 1), xx = rec.x0 + (q & 1);
+              const size_t off = static_cast<size_t>(yy * p.W + xx) * 32;
+              kk[q] = __ldg(ksrc + off); vv[q] = __ldg(vsrc + off);
+            }
+          }
+        };
+        auto blend_store = [&](const TapRec& rec, const uint4 (&kk)[4], const uint4 (&vv)[4], int s) {
           uint4 ko = make_uint4(0, 0, 0, 0), vo = make_uint4(0, 0, 0, 0);
           if (!(HMVIT_BWD_DBG & 16) && (rec.w01 | rec.w23) != 0u) {
             const uint32_t wq[4] = {rec.w01 & 0xffffu, rec.w01 >> 16, rec.w23 & 0xffffu, rec.w23 >> 16};
             ko = make_uint4(bk2[0], bk2[1], bk2[2], bk2[3]);
             vo = make_uint4(bv2[0], bv2[1], bv2[2], bv2[3]);
-            // all eight tap loads of the token are in flight before the first blend (a load-use pair per tap exposed
-            // four global latencies per token; same taps, order and arithmetic as the forward)
-            uint4 kk[4], vv[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              kk[q] = make_uint4(0, 0, 0, 0); vv[q] = make_uint4(0, 0, 0, 0);
-              if (wq[q] != 0u) {
-                const int yy = rec.y0 + (q >> 1), xx = rec.x0 + (q & 1);
-                const size_t off = static_cast<size_t>(yy * p.W + xx) * 32;
-                kk[q] = __ldg(ksrc + off); vv[q] = __ldg(vsrc + off);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 4; ++q) {                      // same taps, order and arithmetic as the forward
               if (wq[q] == 0u) continue;
               const uint32_t w2 = wq[q] | (wq[q] << 16);
               ko.x = hfma2_bf16(w2, kk[q].x, ko.x); ko.y = hfma2_bf16(w2, kk[q].y, ko.y);
@@ -212,7 +212,19 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
           }
           *reinterpret_cast<uint4*>(sK + s * Cfg::LD + u16 * 8) = ko;
           *reinterpret_cast<uint4*>(sV + s * Cfg::LD + u16 * 8) = vo;
-        }
+        };
+        TapRec recs[4];
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) recs[tt] = sTap[tt * 16 + warp * 2 + hlf];
+        uint4 kA[4], vA[4], kB[4], vB[4];
+        load_taps(recs[0], kA, vA);
+        load_taps(recs[1], kB, vB);
+        blend_store(recs[0], kA, vA, 0 * 16 + warp * 2 + hlf);
+        load_taps(recs[2], kA, vA);
+        blend_store(recs[1], kB, vB, 1 * 16 + warp * 2 + hlf);
+        load_taps(recs[3], kB, vB);
+        blend_store(recs[2], kA, vA, 2 * 16 + warp * 2 + hlf);
+        blend_store(recs[3], kB, vB, 3 * 16 + warp * 2 + hlf);
       }
       __syncthreads();
 
