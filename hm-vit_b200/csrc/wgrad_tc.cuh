@@ -160,6 +160,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap m_map, const WgradTcParams p
         v[2 * j] = __ldg(s4);
         v[2 * j + 1] = __ldg(s4 + 1);
       }
+      {   // L2 prefetch of this thread's pieces of the next tile it stages (its loads then see L2, not HBM, latency)
+        const int tn = t + (M_ROWS ? 2 : 1);
+        if (tn < t1) {
+          const int ain = tn / TPA, an = sList[ain] & 0x7fff;
+          const float* nsrc = src_base + (static_cast<size_t>(an) * kC + r0) * p.N + (tn - ain * TPA) * Cfg::KT + u * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + static_cast<size_t>(j) * 32 * p.N));
+        }
+      }
       float4 sv[4];
       if (stats != nullptr) {
         const float4* sp = reinterpret_cast<const float4*>(stats + static_cast<size_t>(a) * p.N + tok0 + u * 8);

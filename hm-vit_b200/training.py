@@ -183,7 +183,9 @@ def forward_train(ops, geo, x, packs, head_pack, num_iters, skip_dead, drop_p=0.
         ops.group_attn(B=B, L=L, H=H, W=W, kind=kind, mode=mode, record_len=rl, cav_mask=cav, T=T, cell=cell,
                        q=qkv[0], k=qkv[1:3], v=qkv[3:5], bk=pk["bk"], bv=pk["bv"], bias_table=pk["bias_table"],
                        out=att, ego_only=dead, lse=lse)
-        xout = torch.zeros_like(xin)
+        # the stage output is written for every active agent and read for active agents only (padded slots pass the input
+        # through at the end, _FusionFn.forward): no zero fill
+        xout = torch.empty_like(xin)
         if drop_p > 0.0:
             dk = dict(B=B, L=L, N=N, record_len=rl, seed=seed, p=drop_p, ego_only=dead)
             tmp = torch.zeros_like(xin)
@@ -240,9 +242,12 @@ def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xl
     common = dict(B=B, L=L, N=N, mode=mode, record_len=rl)
     geo3 = dict(B=B, L=L, N=N, record_len=rl)
     f32 = lambda: torch.zeros(B * L, C_DIM, N, dtype=torch.float32, device=dev)  # noqa: E731
+    # scratch that every kernel writes before it is read, for the active agents only (padded slots are never consumed):
+    # no zero fill (four 346 MB fills per step at the bench shape)
+    scratch = lambda: torch.empty(B * L, C_DIM, N, dtype=torch.float32, device=dev)  # noqa: E731
     zero_b = torch.zeros(2, C_DIM, dtype=torch.float32, device=dev)
     grads = [_zero_grads(dev), _zero_grads(dev)]
-    hp, dh, dz, xp = f32(), f32(), f32(), f32()
+    hp, dh, dz, xp = scratch(), scratch(), scratch(), scratch()
     dmk = f32() if drop_p > 0.0 else None                           # masked copy of a gradient (Dropout adjoint)
     st = torch.zeros(R, 2, dtype=torch.float32, device=dev)
 
@@ -272,8 +277,8 @@ def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xl
         dX = d_xlast.detach().float().reshape(B * L, C_DIM, N).clone()
 
     dO = torch.zeros(R, C_DIM, dtype=rows_dtype, device=dev)
-    dqkv = torch.zeros(5, R, C_DIM, dtype=torch.float32, device=dev)
-    dcat = torch.zeros(5, R, C_DIM, dtype=rows_dtype, device=dev)
+    dqkv = torch.empty(5, R, C_DIM, dtype=torch.float32, device=dev)      # zero-filled before every attention backward
+    dcat = torch.empty(5, R, C_DIM, dtype=rows_dtype, device=dev)         # written whole by the cast
     for s in range(len(sv.qkv) - 1, -1, -1):
         kind = s & 1
         pk, g = packs[kind], grads[kind]

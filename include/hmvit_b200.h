@@ -281,7 +281,9 @@ int hmvit_bwd_colsum(const void* y, int32_t rows_bf16, float* db, int32_t db_str
 int hmvit_dropout(const float* a, const float* resid, float* out, int32_t B, int32_t L, int32_t N, const int32_t* record_len,
                   int32_t ego_only, uint64_t seed, uint32_t stream_id, float p, void* stream);
 
-/* typed weight gradient  dW[type][row0 + m][n] += sum_tok A(tok, m) B(tok, n)  (m, n < 256), tf32 tensor cores */
+/* typed weight gradient  dW[type][row0 + m][n] += sum_tok A(tok, m) B(tok, n)  (m, n < 256): operands rounded to bf16 while
+ * staged, fp32 accumulate; tcgen05 (csrc/wgrad_tc.cuh) when at least one operand is cm, N % 64 == 0 and B*L <= 2048, else the
+ * warp-level wmma kernel (csrc/bwd.cuh) */
 typedef struct {
   int32_t B, L, N;
   const int32_t* mode;
