@@ -138,6 +138,17 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
       const int tok = tok0 + row;
       const bool valid = tok < p.N;
       const float* src = p.a_cm + static_cast<size_t>(a) * kC * p.N + (valid ? tok : 0);
+      {
+        // L2 prefetch of the tile's 256 channel rows (512 B = four 128-byte lines each): the channel batches below are
+        // dependent rounds of 32 loads per thread, eight exposed HBM round trips per tile without it (the fp32 variants run
+        // one CTA per SM, so nothing else hides them)
+        const float* tb = p.a_cm + static_cast<size_t>(a) * kC * p.N + tok0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int e = i * 128 + row, ch = e >> 2, seg = (e & 3) * 32;
+          if (tok0 + seg < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(tb + static_cast<size_t>(ch) * p.N + seg));
+        }
+      }
       float mean = 0.f, rstd = 1.f;
       if constexpr (PRO == PRO_CM_LN) {
         // shifted single pass statistics (shift = first channel) -- biased variance like nn.LayerNorm
