@@ -1019,14 +1019,15 @@ def _train_case(B, L, H, W, record_len, seed, mode=None, skip_dead=True):
 def check_train_grads_small():
     """Whole-module gradients (dL/dx and dL/dtheta of every used parameter) of the CUDA training path against
     torch.autograd through the fp32 CPU oracle.  Stated tolerance (bf16 / tf32 operands, fp32 accumulate):
-    rel-L2 <= 3e-2 per tensor; the forward output keeps the inference tolerance 1e-3."""
+    rel-L2 <= 1.5e-2 per parameter tensor and <= 5e-3 for dL/dx (measured 5.7e-3 / 8.3e-4; the bar was 3e-2 until the
+    end of round 2); the forward output keeps the inference tolerance 1e-3."""
     res = {}
     for tag, args in (("mixed", dict(B=2, L=3, H=16, W=24, record_len=[3, 2], seed=41)),
                       ("nodead", dict(B=1, L=3, H=16, W=24, record_len=[3], seed=42, skip_dead=False)),
                       ("lidar_ego", dict(B=1, L=4, H=32, W=48, record_len=[4], seed=43, mode=[[1, 0, 0, 1]]))):
         r = _train_case(**args)
         res.update({f"{tag}_{k}": v for k, v in r.items()})
-        assert r["fwd_rel_l2"] < 1e-3 and r["dx_rel_l2"] < 3e-2 and r["param_worst_rel_l2"] < 3e-2 and r["params_checked"] > 30, res
+        assert r["fwd_rel_l2"] < 1e-3 and r["dx_rel_l2"] < 5e-3 and r["param_worst_rel_l2"] < 1.5e-2 and r["params_checked"] > 30, res
     return res
 
 
@@ -1184,9 +1185,9 @@ def check_index_probe():
 
 def check_train_grads_48x176():
     """Gradient parity at the BASELINE map size (one scene, 3 mixed agents, 256 x 48 x 176) against torch.autograd through
-    the fp32 CPU oracle; same stated tolerance as check_train_grads_small (3e-2 per tensor, forward 1e-3)."""
+    the fp32 CPU oracle; same stated tolerance as check_train_grads_small (1.5e-2 per parameter tensor, 5e-3 for dL/dx, forward 1e-3)."""
     r = _train_case(B=1, L=3, H=48, W=176, record_len=[3], seed=47, mode=[[1, 0, 1]])
-    assert r["fwd_rel_l2"] < 1e-3 and r["dx_rel_l2"] < 3e-2 and r["param_worst_rel_l2"] < 3e-2 and r["params_checked"] > 30, r
+    assert r["fwd_rel_l2"] < 1e-3 and r["dx_rel_l2"] < 5e-3 and r["param_worst_rel_l2"] < 1.5e-2 and r["params_checked"] > 30, r
     return r
 
 
