@@ -18,7 +18,7 @@ EXPORTS = (
     "hmvit_abi_version", "hmvit_last_error", "hmvit_rowgemm", "hmvit_group_attn", "hmvit_warp_bilinear",
     "hmvit_roi_cav_mask", "hmvit_fusion_workspace_bytes", "hmvit_fusion_forward", "hmvit_fusion_launch_count",
     "hmvit_out_ffn_chain", "hmvit_ffn_head",
-    "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum", "hmvit_bwd_dgrad_cat",
+    "hmvit_bwd_row_stats", "hmvit_bwd_layernorm", "hmvit_bwd_gelu", "hmvit_bwd_cast_bf16", "hmvit_bwd_colsum", "hmvit_bwd_dgrad_cat", "hmvit_bwd_cast_colsum",
     "hmvit_bwd_wgrad", "hmvit_group_attn_bwd", "hmvit_group_attn_workspace_bytes", "hmvit_dropout", "hmvit_attn_records",
     "hmvit_decoder_workspace_bytes", "hmvit_decoder_forward", "hmvit_postprocess_workspace_bytes", "hmvit_postprocess", "hmvit_pillar_scatter",
 )
@@ -162,6 +162,8 @@ def load():
     lib.hmvit_bwd_wgrad.argtypes = [C.POINTER(WgradArgs), vp]
     lib.hmvit_bwd_dgrad_cat.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp]
     lib.hmvit_bwd_dgrad_cat.restype = C.c_int
+    lib.hmvit_bwd_cast_colsum.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    lib.hmvit_bwd_cast_colsum.restype = C.c_int
     lib.hmvit_dropout.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, C.c_uint64, C.c_uint32, C.c_float, vp]
     lib.hmvit_dropout.restype = C.c_int
     lib.hmvit_group_attn_bwd.argtypes = [C.POINTER(AttnBwdArgs), vp]

@@ -783,6 +783,20 @@ extern "C" int hmvit_bwd_wgrad(const HmvitWgradArgs* a, void* stream) {
   return HMVIT_OK;
 }
 
+extern "C" int hmvit_bwd_cast_colsum(const float* src, void* dst, float* db, int32_t db_stride, int32_t B, int32_t L, int32_t N,
+                                     const int32_t* mode, void* stream) {
+  HMVIT_CHECK_ARG(src && dst && db && mode, "bwd_cast_colsum: null pointer");
+  HMVIT_CHECK_ARG(B > 0 && L > 0 && N > 0 && db_stride >= 5 * 256, "bwd_cast_colsum: bad shape (db rows hold 5 x 256 sums)");
+  const long long R = static_cast<long long>(B) * L * N;
+  HMVIT_CHECK_ARG(R < (1ll << 31), "bwd_cast_colsum: too many rows");
+  const int rows_per_block = 256;
+  dim3 grid(static_cast<unsigned>((R + rows_per_block - 1) / rows_per_block), 5);
+  cast_colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint2*>(dst), db,
+                                                                        db_stride, static_cast<int>(R), N, rows_per_block, mode);
+  HMVIT_CHECK_CUDA(cudaGetLastError());
+  return HMVIT_OK;
+}
+
 extern "C" int hmvit_bwd_dgrad_cat(const void* dcat, const void* w0, const void* w1, float* out, int32_t B, int32_t L, int32_t N,
                                    const int32_t* mode, const int32_t* record_len, void* stream) {
   HMVIT_CHECK_ARG(B > 0 && L > 0 && N > 0 && B * L <= DgradCatCfg::MAX_AGENTS, "bwd_dgrad_cat: bad shape (B*L <= 2048)");

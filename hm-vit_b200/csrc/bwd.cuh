@@ -104,6 +104,40 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float4* __restrict
   }
 }
 
+// fp32 -> bf16 of the five gradient planes [5][R][256] of the fused Q | K' | V' projection AND their typed column sums in
+// the same pass (the bias gradient of the projection): db[type(agent of the row)][p * 256 + c] += src[p][row][c].  Replaces
+// cast_bf16_kernel + five colsum_rows launches that re-read the bf16 copy.  Rows of padded slots must be zero (they are:
+// the attention backward accumulates into a zero-filled buffer and never touches them), so no validity test is needed.
+// grid (ceil(R / rows_per_block), 5), 256 threads: thread = (row lane tid / 64, 4-channel group tid % 64).
+__global__ void __launch_bounds__(256) cast_colsum_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, float* __restrict__ db,
+                                                          int db_stride, int R, int N, int rows_per_block, const int* __restrict__ mode) {
+  const int pl = blockIdx.y, cg = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(R, r0 + rows_per_block);
+  const size_t base = static_cast<size_t>(pl) * R;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  int ag = r0 / N, nb = (ag + 1) * N;                            // agent of the current row, first row of the next agent
+  bool t1 = __ldg(mode + ag) != 0;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += 4) {
+    const float4 v = __ldg(src + (base + r) * 64 + cg);
+    dst[(base + r) * 64 + cg] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    while (r >= nb) { ++ag; nb += N; t1 = __ldg(mode + ag) != 0; }
+    if (t1) { a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w; }
+    else { a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w; }
+  }
+  __shared__ float4 sAcc[2][4][64];
+  sAcc[0][rl][cg] = a0; sAcc[1][rl][cg] = a1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int t = threadIdx.x >> 6;
+    float4 s = sAcc[t][0][cg];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) { const float4 o = sAcc[t][i][cg]; s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w; }
+    float* d = db + static_cast<size_t>(t) * db_stride + pl * kC + cg * 4;
+    atomicAdd(d, s.x); atomicAdd(d + 1, s.y); atomicAdd(d + 2, s.z); atomicAdd(d + 3, s.w);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // bias gradients: db[type][c] += sum over the tokens of every active agent of that type
 // ------------------------------------------------------------------------------------------

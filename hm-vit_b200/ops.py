@@ -174,6 +174,14 @@ def bwd_cast_bf16(src, dst):
     return dst
 
 
+def bwd_cast_colsum(src, dst, db, *, B, L, N, mode):
+    """dst = bf16(src) for the five gradient planes src (5, B*L*N, 256) fp32 and, in the same pass, their typed column sums:
+    db[type, p*256 + c] += sum over the rows of agents of that type (db (2, >= 1280) fp32).  Rows of padded slots must be 0."""
+    _lib.check(_lib.load().hmvit_bwd_cast_colsum(src.data_ptr(), dst.data_ptr(), db.data_ptr(), db.stride(0), B, L, N,
+                                                 mode.data_ptr(), _stream()))
+    return dst
+
+
 def bwd_colsum(y, db, *, B, L, N, mode, record_len, ego_only=False):
     """db[type] += sum over tokens of y; y cm fp32 (B*L, 256, N) or bf16 rows (B*L*N, 256); db (2, >=256) fp32 view whose
     first 256 columns are accumulated (row stride = db.stride(0))."""

@@ -327,12 +327,11 @@ def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xl
                            q=qkv[0], k=qkv[1:3], v=qkv[3:5], bk=pk["bk"], bv=pk["bv"], bias_table=pk["bias_table"],
                            o=att, d_o=dO, lse=lse, dq=dqkv[0], dk=dqkv[1:3], dv=dqkv[3:5],
                            dbk=g["bk"], dbv=g["bv"], dbias_table=g["bias_table"], ego_only=dead)
-        ops.bwd_cast_bf16(dqkv, dcat)
+        ops.bwd_cast_colsum(dqkv, dcat, g["bcat"], B=B, L=L, N=N, mode=mode)   # bf16 copy + bias gradient of the projection
         # ---- typed LayerNorm + Q / K' / V' projection (all valid agents: they are K/V sources) ----
         ops.bwd_row_stats(xin, st, **geo3)
         for p in range(5):
             ops.bwd_wgrad(dcat[p], xin, g["wcat"], b_stats=st, row0=p * C_DIM, **common)
-            ops.bwd_colsum(dcat[p], g["bcat"][:, p * C_DIM:], **common)
         ops.bwd_dgrad_cat(dcat, pk["wcatT_0"], pk["wcatT_1"], dz, **common)
         ops.bwd_layernorm(dz, xin, st, dX, dX, **geo3)                 # dX: gradient w.r.t. the stage input
     return dX, grads, head_grads

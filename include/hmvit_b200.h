@@ -268,6 +268,11 @@ int hmvit_bwd_layernorm(const float* dz, const float* x, const float* stats, con
 int hmvit_bwd_gelu(float* hp, float* dh, size_t n, void* stream);
 /* dst[i] = bf16(src[i]), n floats (n % 4 == 0) */
 int hmvit_bwd_cast_bf16(const float* src, void* dst, size_t n, void* stream);
+/* dst = bf16(src) over the five gradient planes src [5][B*L*N][256] of the fused Q | K' | V' projection, and in the same pass
+ * their typed column sums (the projection's bias gradient): db[type(agent of the row)*db_stride + p*256 + c] += src[p][row][c].
+ * Rows of padded slots must be zero (hmvit_group_attn_bwd accumulates into a zero-filled buffer and never touches them). */
+int hmvit_bwd_cast_colsum(const float* src, void* dst, float* db, int32_t db_stride, int32_t B, int32_t L, int32_t N,
+                          const int32_t* mode, void* stream);
 /* bias gradient: db[type*db_stride + c] += sum over tokens of y;  y is cm fp32 (rows_bf16 == 0) or bf16 rows */
 int hmvit_bwd_colsum(const void* y, int32_t rows_bf16, float* db, int32_t db_stride, int32_t B, int32_t L, int32_t N,
                      const int32_t* mode, const int32_t* record_len, int32_t ego_only, void* stream);

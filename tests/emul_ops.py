@@ -211,6 +211,14 @@ def _operand(t, ai, N):
     return t[ai * N:(ai + 1) * N].float() if t.dim() == 2 else t[ai].t()
 
 
+def bwd_cast_colsum(src, dst, db, *, B, L, N, mode):
+    dst.copy_(src.to(dst.dtype))
+    m = mode.reshape(-1)
+    for ai in range(B * L):
+        db[int(m[ai] != 0), :5 * C] += src[:, ai * N:(ai + 1) * N].float().sum(1).reshape(-1)
+    return dst
+
+
 def bwd_dgrad_cat(dcat, w0, w1, out, *, B, L, N, mode, record_len):
     w = (w0.float(), w1.float())
     mode = mode.reshape(-1)

@@ -843,6 +843,26 @@ def check_bwd_dgrad_cat():
     return res
 
 
+def check_bwd_cast_colsum():
+    """bf16 copy of the five gradient planes + their typed column sums in one pass (cast_colsum_kernel) vs the emulation: the copy
+    bit-exact, the sums to fp32 summation order (random data in every slot, so padded slots count on both sides)."""
+    ops = pkg().ops
+    g = _geo_small(seed=12, H=24, W=24)
+    B, L, N = g["B"], g["L"], g["N"]
+    gen = torch.Generator().manual_seed(6)
+    src = torch.randn(5, B * L * N, 256, generator=gen)
+    ref_dst, ref_db = torch.empty(5, B * L * N, 256, dtype=torch.bfloat16), torch.full((2, 1300), 0.25)
+    EM.bwd_cast_colsum(src, ref_dst, ref_db, B=B, L=L, N=N, mode=g["mode"])
+    dst, db = torch.empty(5, B * L * N, 256, dtype=torch.bfloat16, device=DEV), torch.full((2, 1300), 0.25, device=DEV)
+    ops.bwd_cast_colsum(src.to(DEV), dst, db, B=B, L=L, N=N, mode=g["mode"].to(DEV))
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu(), ref_dst)
+    assert bool((db[:, 1280:] == 0.25).all()), "columns past the 5 x 256 sums must stay untouched"
+    res = {"colsum_max_rel": max_rel(db.cpu()[:, :1280], ref_db[:, :1280])}
+    assert res["colsum_max_rel"] < 2e-5, res
+    return res
+
+
 def check_bwd_lin_variants():
     """the row-GEMM variants the backward uses (7-10) against the emulation with equally rounded operands."""
     p = pkg()
@@ -1066,7 +1086,7 @@ def check_train_api():
 
 
 CHECKS.update({"bwd_small_kernels": check_bwd_small_kernels, "bwd_wgrad": check_bwd_wgrad,
-               "bwd_lin_variants": check_bwd_lin_variants, "bwd_dgrad_cat": check_bwd_dgrad_cat, "attn_bwd": check_attn_bwd,
+               "bwd_lin_variants": check_bwd_lin_variants, "bwd_dgrad_cat": check_bwd_dgrad_cat, "bwd_cast_colsum": check_bwd_cast_colsum, "attn_bwd": check_attn_bwd,
                "train_grads_small": check_train_grads_small, "train_api": check_train_api,
                "attn_split_vs_single": check_attn_split_vs_single})
 
