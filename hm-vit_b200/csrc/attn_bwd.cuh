@@ -55,7 +55,7 @@ struct AttnBwdCfg {
   static constexpr int LD = 136;                                  // bf16 elements per tile row (128 + 8 pad)
   static constexpr int TILE_BYTES = kS * LD * 2;                  // 17408
   static constexpr int SCR_BYTES = 4096 + 4096 + 2048 + 2048;     // per warp: S | dP (fp32 [64][16]) | P | dS (bf16 [64][16])
-  static constexpr int OFF_SCR = 4 * TILE_BYTES;
+  static constexpr int OFF_SCR = 6 * TILE_BYTES;                  // Q | dO | (Kg | Vg) x 2: the re-gathered tiles are double-buffered
   static constexpr int OFF_BIAS = OFF_SCR + 8 * SCR_BYTES;        // [4][232] fp32, log2 domain
   static constexpr int OFF_BGRAD = OFF_BIAS + kHG * kBiasStride * 4;
   static constexpr int OFF_D = OFF_BGRAD + 8 * kBiasStride * 4;   // bias gradient: one private [232] table per warp; D: [4][64]
@@ -85,8 +85,7 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
   extern __shared__ __align__(128) uint8_t smem[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem);
   __nv_bfloat16* sdO = reinterpret_cast<__nv_bfloat16*>(smem + Cfg::TILE_BYTES);
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(smem + 2 * Cfg::TILE_BYTES);
-  __nv_bfloat16* sV = reinterpret_cast<__nv_bfloat16*>(smem + 3 * Cfg::TILE_BYTES);
+  __nv_bfloat16* sKV = reinterpret_cast<__nv_bfloat16*>(smem + 2 * Cfg::TILE_BYTES);      // [2 buffers][Kg | Vg]
   uint8_t* scr = smem + Cfg::OFF_SCR + warp * Cfg::SCR_BYTES;
   float* sS = reinterpret_cast<float*>(scr);                    // [64][16] logits, later dKg chunk [16][32]
   float* sdP = reinterpret_cast<float*>(scr + 4096);            // [64][16] dP, later dVg chunk [16][32]
@@ -139,6 +138,7 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
   const size_t plane = R * 32;                                   // uint4 units per te plane
   const int ch = hgc * 128 + hl * 32 + lane;                     // channel this lane scatters
 
+  int nvis_done = 0;                                             // sources processed so far (CTA-uniform): tile buffer parity
   for (int j0 = 0; j0 < nrec; j0 += kMaxSrc) {
     const int nsrc = min(kMaxSrc, nrec - j0);
     __syncthreads();
@@ -166,6 +166,12 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
     for (int js = 0; js < nsrc; ++js) {
       const int j = j0 + js;
       if (sAnyVis[js] == 0) continue;
+      // Two tile buffers: a warp that has finished source j gathers source j + 1 into the other buffer while slower warps
+      // still multiply source j -- one CTA barrier per source (tile complete) instead of two.  The buffer written now was
+      // last read for the source before the previous one, and every warp passed the previous source's barrier after that.
+      __nv_bfloat16* sK = sKV + (nvis_done & 1) * (2 * Cfg::TILE_BYTES / 2);
+      __nv_bfloat16* sV = sK + Cfg::TILE_BYTES / 2;
+      ++nvis_done;
       const TapRec* sTap = sTapAll + js * kS;
       const int tj = p.mode[b * p.L + j] != 0 ? 1 : 0;
       // ---- re-gather Kg / Vg of source j (same bf16 blend as the forward) ----
@@ -379,7 +385,6 @@ __global__ void __launch_bounds__(AttnBwdCfg::THREADS, 1) group_attn_bwd_kernel(
           red_add_v4(p.dbv + (te * 2 + tj) * kC + ch4, bsum_v4.x, bsum_v4.y, bsum_v4.z, bsum_v4.w);
         }
       }
-      __syncthreads();                                           // sK / sV are rewritten for the next source
     }
   }
 
