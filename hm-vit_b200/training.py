@@ -6,8 +6,10 @@ forward runs the same sm_100a kernels as inference, stage by stage, keeping per 
 (fp32), the projected Q / K' / V' rows, the attention output and the softmax log-sum-exp; the backward is the
 adjoint of the RESTRUCTURED forward:
 
-  * input-gradient GEMMs  = the tcgen05 row-GEMM with transposed weights (ops.rowgemm variants 7-10);
-  * weight gradients      = ops.bwd_wgrad (typed, tensor cores), bias gradients = ops.bwd_colsum;
+  * input-gradient GEMMs  = the tcgen05 row-GEMM with transposed weights (ops.rowgemm variants 7-10); the five planes of the
+                            fused Q | K' | V' projection as ONE K = 1280 GEMM (ops.bwd_dgrad_cat);
+  * weight gradients      = ops.bwd_wgrad (typed, tcgen05 with the accumulator in tensor memory), bias gradients =
+                            ops.bwd_colsum / ops.bwd_cast_colsum (the projection's, in the pass that casts its gradient planes);
   * LayerNorm / GELU      = ops.bwd_layernorm / ops.bwd_gelu;
   * attention             = ops.group_attn_bwd (re-gathers K'/V', scatters dK'/dV' through the bilinear taps).
 

@@ -793,7 +793,9 @@ def check_bwd_small_kernels():
 
 
 def check_bwd_wgrad():
-    """typed weight gradient, all four operand-layout combinations (+ on-the-fly normalisation); tf32 operands."""
+    """typed weight gradient, all operand-layout combinations (+ on-the-fly normalisation): cm x cm, cm x cm + LN and rows x cm run the
+    tcgen05 kernel (csrc/wgrad_tc.cuh), cm x rows the same kernel with the operands exchanged, rows x rows the wmma kernel (csrc/bwd.cuh);
+    operands are rounded to bf16 while staged, fp32 accumulate."""
     ops = pkg().ops
     g = _geo_small(seed=8)
     B, L, N = g["B"], g["L"], g["N"]
