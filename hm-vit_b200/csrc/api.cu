@@ -168,6 +168,7 @@ extern "C" int hmvit_rowgemm(int variant, const HmvitRowGemmArgs* a, void* strea
       return launch_rowgemm<4, PRO_CM_CAST, EPI_CM_STORE>(m0, m1, p, st);
     case HMVIT_GEMM_LN_LIN_CM:
       p.a_cm = static_cast<const float*>(a->a); p.out_cm = static_cast<float*>(a->out);
+      p.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
       p.tile_ego_only = a->ego_only ? 1 : 0;
       return launch_rowgemm<4, PRO_CM_LN, EPI_CM_STORE>(m0, m1, p, st);
     case HMVIT_GEMM_LIN_CM:

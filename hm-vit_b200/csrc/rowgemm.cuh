@@ -42,6 +42,7 @@ struct RowGemmParams {
   const float* ln_gamma;       // [2][256]
   const float* ln_beta;        // [2][256]
   float ln_eps;
+  const float2* ln_stats;      // PRO_CM_LN, optional: [B*L][N] (mean, rstd) of every row of A (skips the statistics pass)
   // epilogue
   const float* bias;           // [2][Ntot]
   __nv_bfloat16* out_rows;     // EPI_ROWS_BF16: [n_chunks/2][B*L*N][256]
@@ -150,7 +151,9 @@ rowgemm_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant_
         }
       }
       float mean = 0.f, rstd = 1.f;
-      if constexpr (PRO == PRO_CM_LN) {
+      if (PRO == PRO_CM_LN && p.ln_stats != nullptr) {
+        if (valid) { const float2 st = __ldg(p.ln_stats + static_cast<size_t>(a) * p.N + tok); mean = st.x; rstd = st.y; }
+      } else if constexpr (PRO == PRO_CM_LN) {
         // shifted single pass statistics (shift = first channel) -- biased variance like nn.LayerNorm
         const float s0 = valid ? __ldg(src) : 0.f;
         float sum = 0.f, sq = 0.f;

@@ -297,7 +297,7 @@ def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xl
                         ego_only=dead, **common)
         ops.bwd_row_stats(xp, st, ego_only=dead, **geo3)
         ops.rowgemm(_lib.GEMM_LN_LIN_CM, n_out=C_DIM, a=xp, w0=pk["w1_0"], w1=pk["w1_1"], bias=pk["b1"], out=hp,
-                    ego_only=dead, **common)
+                    ego_only=dead, ln_stats=st, **common)
         # ---- FFN: x'' = x' + [Dropout](W2 [Dropout](gelu(W1' LN(x') + b1')) + b2) ----
         dff = dX                                                     # gradient of the FFN output
         if drop_p > 0.0:

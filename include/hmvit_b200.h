@@ -77,7 +77,7 @@ typedef struct {
   float ln_eps;
   const float* resid;         /* fp32 cm (OUT, FFN2) */
   void* out;                  /* see variant */
-  const float* ln_stats;      /* QKV only, optional: [B*L][N][2] (mean, rstd) of every row of `a`, as written by
+  const float* ln_stats;      /* QKV and LN_LIN_CM only, optional: [B*L][N][2] (mean, rstd) of every row of `a`, as written by
                                  hmvit_out_ffn_chain(stats_out); NULL = compute the statistics in the kernel */
 } HmvitRowGemmArgs;
 
