@@ -170,6 +170,7 @@ def forward_train(ops, geo, x, packs, head_pack, num_iters, skip_dead, drop_p=0.
     common = dict(B=B, L=L, N=N, mode=mode, record_len=rl)
     sv = _Saved()
     sv.xs, sv.qkv, sv.att, sv.lse, sv.dead = [x], [], [], [], []
+    sv.stats = [None]                        # LayerNorm statistics of sv.xs[s] when the producing chain launch wrote them
     head = head_pack is not None
     n_stage = 2 * num_iters
     for s in range(n_stage):
@@ -179,7 +180,7 @@ def forward_train(ops, geo, x, packs, head_pack, num_iters, skip_dead, drop_p=0.
         xin = sv.xs[-1]
         qkv = torch.empty(5, R, C_DIM, dtype=rows_dtype, device=dev)
         ops.rowgemm(_lib.GEMM_QKV, n_out=5 * C_DIM, a=xin, w0=pk["wqkv0"], w1=pk["wqkv1"], bias=pk["bcat"], out=qkv,
-                    ego_only=dead, **common)
+                    ego_only=dead, ln_stats=sv.stats[-1], **common)
         att = torch.empty(R, C_DIM, dtype=rows_dtype, device=dev)
         lse = torch.empty(R, 8, dtype=torch.float32, device=dev)
         ops.group_attn(B=B, L=L, H=H, W=W, kind=kind, mode=mode, record_len=rl, cav_mask=cav, T=T, cell=cell,
@@ -188,6 +189,7 @@ def forward_train(ops, geo, x, packs, head_pack, num_iters, skip_dead, drop_p=0.
         # the stage output is written for every active agent and read for active agents only (padded slots pass the input
         # through at the end, _FusionFn.forward): no zero fill
         xout = torch.empty_like(xin)
+        st_next = None
         if drop_p > 0.0:
             dk = dict(B=B, L=L, N=N, record_len=rl, seed=seed, p=drop_p, ego_only=dead)
             tmp = torch.zeros_like(xin)
@@ -205,9 +207,13 @@ def forward_train(ops, geo, x, packs, head_pack, num_iters, skip_dead, drop_p=0.
             ops.dropout(tmp, xout, resid=xp, stream_id=_drop_stream(s, 2), **dk)         # x'' = x' + Dropout(W2 h + b2)
             del tmp, hid, xp
         else:
+            # the chain kernel hands the next stage the LayerNorm statistics of its output rows (as the inference path does):
+            # no statistics pass in the next QKV launch nor in the backward of the next stage
+            st_next = None if dead else torch.empty(R, 2, dtype=torch.float32, device=dev)
             ops.out_ffn_chain(o=att, resid=xin, out=xout, wa0=pk["wa0"], wa1=pk["wa1"], ba=pk["ba"],
                               w1_0=pk["w1h_0"], w1_1=pk["w1h_1"], b1=pk["b1"], w2_0=pk["w2h_0"], w2_1=pk["w2h_1"], b2=pk["b2"],
-                              ego_only=dead, **common)
+                              ego_only=dead, stats_out=st_next, **common)
+        sv.stats.append(st_next)
         sv.qkv.append(qkv); sv.att.append(att); sv.lse.append(lse); sv.dead.append(dead); sv.xs.append(xout)
     out = None
     if head:
@@ -331,11 +337,13 @@ def backward(ops, geo, sv, packs, head_pack, d_out: Optional[torch.Tensor], d_xl
                            dbk=g["bk"], dbv=g["bv"], dbias_table=g["bias_table"], ego_only=dead)
         ops.bwd_cast_colsum(dqkv, dcat, g["bcat"], B=B, L=L, N=N, mode=mode)   # bf16 copy + bias gradient of the projection
         # ---- typed LayerNorm + Q / K' / V' projection (all valid agents: they are K/V sources) ----
-        ops.bwd_row_stats(xin, st, **geo3)
+        st_in = sv.stats[s]                                            # saved by the forward's chain launch, else computed here
+        if st_in is None:
+            st_in = ops.bwd_row_stats(xin, st, **geo3)
         for p in range(5):
-            ops.bwd_wgrad(dcat[p], xin, g["wcat"], b_stats=st, row0=p * C_DIM, **common)
+            ops.bwd_wgrad(dcat[p], xin, g["wcat"], b_stats=st_in, row0=p * C_DIM, **common)
         ops.bwd_dgrad_cat(dcat, pk["wcatT_0"], pk["wcatT_1"], dz, **common)
-        ops.bwd_layernorm(dz, xin, st, dX, dX, **geo3)                 # dX: gradient w.r.t. the stage input
+        ops.bwd_layernorm(dz, xin, st_in, dX, dX, **geo3)              # dX: gradient w.r.t. the stage input
     return dX, grads, head_grads
 
 

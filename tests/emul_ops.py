@@ -89,6 +89,11 @@ def out_ffn_chain(*, B, L, N, mode, record_len, o, resid, out, wa0, wa1, ba, w1_
         x1 = resid[ai].t() + o[ai * N:(ai + 1) * N].float() @ wa[t].t() + ba[t]
         h = F.gelu(_ln(x1, ln_eps) @ w1[t].t() + b1[t])
         out[ai] = (x1 + h @ w2[t].t() + b2[t]).t()
+        if stats_out is not None:                                    # (mean, rstd) of every output row, for the next stage's LayerNorm
+            v = out[ai]
+            st = stats_out.view(B * L, N, 2)
+            st[ai, :, 0] = v.mean(0)
+            st[ai, :, 1] = torch.rsqrt(v.var(0, unbiased=False) + ln_eps)
     return out
 
 
